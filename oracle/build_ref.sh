@@ -1,0 +1,46 @@
+#!/usr/bin/env bash
+# oracle/build_ref.sh -- TEST INFRASTRUCTURE.
+# Compiles the UNMODIFIED reference (SheffieldML/GPc) from the sources WHERE THEY LIE under
+# $GPC_REFERENCE (default /root/reference) into oracle/_ref/ (git-ignored, travels with gpurun):
+#   oracle/_ref/libgpcref.so   reference objects + oracle/ref_driver.cpp (ctypes facade)
+#   oracle/_ref/gp, gplvm      the reference CLI front-ends (for end-to-end trajectories)
+# No reference source is copied into this repository.  The reference's own build system is not used
+# (it wants gfortran + system BLAS): three shims instead:
+#   1. -std=gnu++98 (dynamic exception specs, ostream->void*)
+#   2. ndlfortran.c (the shipped f2c translation) with oracle/shim/f2c.h; lbfgs_ stubbed
+#   3. BLAS/LAPACK = the scipy wheel's LP64 OpenBLAS (symbols prefixed scipy_) via a generated blasmap.h
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${GPC_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$REF" ]; then
+  echo "build_ref: $REF not present (GPU box?) - keeping prebuilt oracle/_ref" >&2
+  exit 0
+fi
+mkdir -p "$OUT/obj"
+PY="${PYTHON:-python3}"
+SP=$($PY -c "import scipy,os;print(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)),'scipy.libs'))")
+OB=$(ls "$SP"/libscipy_openblas-*.so | head -1)
+# the 21 Fortran symbols declared in the reference's lapack.h:17-232
+for s in dsyev dsysv dgetrf dgetri dpotrf dpotri dswap dcopy dscal daxpy ddot dnrm2 dgemv dsymv dger dsyr dgemm dsyrk dtrmm dtrsm dsymm; do
+  echo "#define ${s}_ scipy_${s}_"
+done > "$OUT/obj/blasmap.h"
+CXXF="-std=gnu++98 -O3 -fPIC -w -D_LINUX -include $OUT/obj/blasmap.h -I$REF"
+SRCS="CClctrl CGp CGplvm CMatrix CNoise ndlutil ndlstrutil CTransform COptimisable CKern CDist ndlassert gp gplvm"
+pids=()
+for f in $SRCS; do
+  if [ ! -f "$OUT/obj/$f.o" ] || [ "$REF/$f.cpp" -nt "$OUT/obj/$f.o" ]; then
+    g++ $CXXF -c "$REF/$f.cpp" -o "$OUT/obj/$f.o" &
+    pids+=($!)
+  fi
+done
+gcc -O3 -fPIC -w -I"$HERE/shim" -I"$REF" -c "$REF/ndlfortran.c" -o "$OUT/obj/ndlfortran.o"
+gcc -O2 -fPIC -c "$HERE/shim/lbfgs_stub.c" -o "$OUT/obj/lbfgs_stub.o"
+g++ $CXXF -c "$HERE/ref_driver.cpp" -o "$OUT/obj/ref_driver.o"
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+cd "$OUT/obj"
+COMMON="CClctrl.o CMatrix.o ndlfortran.o lbfgs_stub.o CNoise.o ndlutil.o ndlstrutil.o CTransform.o COptimisable.o CKern.o CDist.o ndlassert.o"
+g++ -shared -o "$OUT/libgpcref.so" ref_driver.o CGp.o CGplvm.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
+g++ -o "$OUT/gp" gp.o CGp.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
+g++ -o "$OUT/gplvm" gplvm.o CGplvm.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
+echo "build_ref: built $OUT/libgpcref.so, gp, gplvm (OpenBLAS: $OB)"
