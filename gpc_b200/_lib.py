@@ -1,0 +1,117 @@
+"""ctypes binding of libgpc_b200.so (include/gpc_b200.h).  No fallbacks: if the CUDA library is missing or
+there is no CUDA device every compute call raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpc_b200.so")
+_lib = None
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+i64 = C.c_int64
+
+
+class KComp(C.Structure):
+    _fields_ = [("type", C.c_int), ("nparams", C.c_int), ("params", c_double_p), ("degree", C.c_double)]
+
+
+class GpcError(RuntimeError):
+    pass
+
+
+class MatrixNonPosDef(GpcError):
+    """mirrors ndlexceptions::MatrixNonPosDef (thrown by CMatrix::potrf, CMatrix.cpp:378)"""
+
+    def __init__(self, info):
+        super().__init__("matrix is non positive definite (info=%d)" % info)
+        self.info = info
+
+
+# every symbol include/gpc_b200.h declares (tests/test_abi_cpu.py checks the .so exports all of them)
+SYMBOLS = [
+    "gpc_last_error", "gpc_device_count", "gpc_kern_nparams", "gpc_kern_transform", "gpc_transform_atox",
+    "gpc_transform_xtoa", "gpc_transform_gradfact", "gpc_ctx_create", "gpc_ctx_destroy", "gpc_ctx_set_stream",
+    "gpc_ctx_get_stream", "gpc_ctx_sync", "gpc_ctx_launch_count", "gpc_set_X", "gpc_set_M", "gpc_set_Y",
+    "gpc_kern_build", "gpc_kern_cross", "gpc_kern_diag", "gpc_add_diag", "gpc_potrf", "gpc_jitchol",
+    "gpc_solve_alpha", "gpc_inverse", "gpc_alpha_from_inverse", "gpc_grad", "gpc_kern_grad", "gpc_posterior",
+    "gpc_eval", "gpc_download", "gpc_last_timings", "gpc_dpotrf", "gpc_dpotri", "gpc_dtrsm", "gpc_dsyrk",
+    "gpc_dgemm", "gpc_dsymv", "gpc_bench_dmma_peak", "gpc_bench_syrk",
+]
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (python -m gpc_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GpcError("libgpc_b200.so not built: run `python -m gpc_b200.build` (needs nvcc); there is no CPU path")
+    L = C.CDLL(LIB_PATH)
+    L.gpc_last_error.restype = C.c_char_p
+    L.gpc_transform_atox.restype = C.c_double
+    L.gpc_transform_atox.argtypes = [C.c_int, C.c_double]
+    L.gpc_transform_xtoa.restype = C.c_double
+    L.gpc_transform_xtoa.argtypes = [C.c_int, C.c_double]
+    L.gpc_transform_gradfact.restype = C.c_double
+    L.gpc_transform_gradfact.argtypes = [C.c_int, C.c_double]
+    L.gpc_ctx_get_stream.restype = C.c_void_p
+    L.gpc_ctx_get_stream.argtypes = [C.c_void_p]
+    L.gpc_ctx_launch_count.restype = i64
+    L.gpc_ctx_launch_count.argtypes = [C.c_void_p]
+    L.gpc_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, i64, C.c_int, C.c_int]
+    L.gpc_ctx_destroy.argtypes = [C.c_void_p]
+    L.gpc_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.gpc_ctx_sync.argtypes = [C.c_void_p]
+    L.gpc_set_X.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_int, i64]
+    L.gpc_set_M.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_int, i64]
+    L.gpc_set_Y.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_int, i64, C.c_void_p, C.c_void_p]
+    L.gpc_kern_build.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int]
+    L.gpc_kern_cross.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, i64, i64, C.c_void_p, i64]
+    L.gpc_kern_diag.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, i64, i64, C.c_void_p]
+    L.gpc_add_diag.argtypes = [C.c_void_p, C.c_double]
+    L.gpc_potrf.argtypes = [C.c_void_p, c_int_p, c_double_p]
+    L.gpc_jitchol.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
+    L.gpc_solve_alpha.argtypes = [C.c_void_p, c_double_p]
+    L.gpc_inverse.argtypes = [C.c_void_p]
+    L.gpc_alpha_from_inverse.argtypes = [C.c_void_p, c_double_p]
+    L.gpc_grad.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, C.c_void_p]
+    L.gpc_kern_grad.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, i64, C.c_void_p, C.c_void_p]
+    L.gpc_posterior.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, i64, i64, C.c_void_p, C.c_void_p]
+    L.gpc_eval.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gpc_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, i64]
+    L.gpc_last_timings.argtypes = [C.c_void_p, C.c_void_p]
+    L.gpc_dpotrf.argtypes = [C.c_int, C.c_char, i64, C.c_void_p, i64, c_int_p]
+    L.gpc_dpotri.argtypes = [C.c_int, C.c_char, i64, C.c_void_p, i64, c_int_p]
+    L.gpc_dtrsm.argtypes = [C.c_int, C.c_char, C.c_char, C.c_char, C.c_char, i64, i64, C.c_double, C.c_void_p, i64,
+                            C.c_void_p, i64]
+    L.gpc_dsyrk.argtypes = [C.c_int, C.c_char, C.c_char, i64, i64, C.c_double, C.c_void_p, i64, C.c_double,
+                            C.c_void_p, i64]
+    L.gpc_dgemm.argtypes = [C.c_int, C.c_char, C.c_char, i64, i64, i64, C.c_double, C.c_void_p, i64, C.c_void_p, i64,
+                            C.c_double, C.c_void_p, i64]
+    L.gpc_dsymv.argtypes = [C.c_int, C.c_char, i64, C.c_double, C.c_void_p, i64, C.c_void_p, C.c_double, C.c_void_p]
+    L.gpc_bench_dmma_peak.argtypes = [C.c_int, c_double_p]
+    L.gpc_bench_syrk.argtypes = [C.c_int, i64, i64, C.c_int, c_double_p]
+    _lib = L
+    return L
+
+
+def check(rc):
+    """<0 -> GpcError with the library's message; >0 (numerical info) is returned to the caller."""
+    if rc < 0:
+        raise GpcError(lib().gpc_last_error().decode() or ("gpc error %d" % rc))
+    return rc
+
+
+def fmat(a):
+    """column-major fp64 view/copy (CMatrix layout, CMatrix.h:268)"""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    return np.asfortranarray(a)
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,737 @@
+// api.cu -- the C ABI of libgpc_b200.so (include/gpc_b200.h): device context, the recursive blocked
+// Cholesky / triangular solves / SPD inverse built on the DMMA GEMM engine (dense.cu), the fused GP
+// evaluation, and the lapack.h-level drop-ins.  Host code only orchestrates launches; there is no CPU
+// fallback: every entry point needs a CUDA device.
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+
+namespace gpc {
+
+static thread_local std::string g_error;
+void set_error(const std::string& s) { g_error = s; }
+
+#define GPC_CHECK(expr)             \
+  do {                              \
+    int _rc = (expr);               \
+    if (_rc != GPC_OK) return _rc;  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// Recursive blocked algorithms.  All dimensions are multiples of TILE; recursion splits at multiples of TILE
+// so that (almost) all flops are large-k GEMM/SYRK calls; the TILE x TILE leaves use the inverse of the
+// factor's diagonal block (Dinv, written by the potrf leaf), turning the leaf TRSM into a GEMM as well.
+// ------------------------------------------------------------------------------------------------------
+static inline int64_t split(int64_t n) { return (n / TILE / 2) * TILE; }
+
+// X L' = B, in place.  B: m x n, L: n x n lower; dbase = index of L's first row/col in the full factor
+int trsm_rlt(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n,
+                    int64_t dbase) {
+  if (m <= 0) return GPC_OK;
+  if (n == TILE) {
+    GemmCall g{B, d.Dinv + dbase * TILE, B, ldb, TILE, ldb, m, TILE, TILE, 1.0, 0.0, false, false, false};
+    return launch_gemm(g, d.s, d.launches);  // force-128 rule inside launch_gemm keeps in-place safe (n == TILE)
+  }
+  int64_t n1 = split(n), n2 = n - n1;
+  GPC_CHECK(trsm_rlt(d, B, ldb, m, L, ldl, n1, dbase));
+  GemmCall g{B, L + n1, B + n1 * ldb, ldb, ldl, ldb, m, n2, n1, -1.0, 1.0, false, false, false};
+  GPC_CHECK(launch_gemm(g, d.s, d.launches));
+  return trsm_rlt(d, B + n1 * ldb, ldb, m, L + n1 + n1 * ldl, ldl, n2, dbase + n1);
+}
+
+// X L = B, in place.
+int trsm_rln(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n,
+                    int64_t dbase) {
+  if (m <= 0) return GPC_OK;
+  if (n == TILE) {
+    GemmCall g{B, d.Dinv + dbase * TILE, B, ldb, TILE, ldb, m, TILE, TILE, 1.0, 0.0, false, true, false};
+    return launch_gemm(g, d.s, d.launches);
+  }
+  int64_t n1 = split(n), n2 = n - n1;
+  GPC_CHECK(trsm_rln(d, B + n1 * ldb, ldb, m, L + n1 + n1 * ldl, ldl, n2, dbase + n1));
+  GemmCall g{B + n1 * ldb, L + n1, B, ldb, ldl, ldb, m, n1, n2, -1.0, 1.0, false, true, false};
+  GPC_CHECK(launch_gemm(g, d.s, d.launches));
+  return trsm_rln(d, B, ldb, m, L, ldl, n1, dbase);
+}
+
+// in-place lower Cholesky of A (n x n), only the lower triangle is referenced / written
+int potrf_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base) {
+  if (n == TILE)
+    return launch_potrf_leaf(A, lda, d.Dinv + base * TILE, d.info, (int)base, d.nvalid - base, d.logdet, d.s,
+                             d.launches);
+  int64_t n1 = split(n), n2 = n - n1;
+  GPC_CHECK(potrf_rec(d, A, lda, n1, base));
+  GPC_CHECK(trsm_rlt(d, A + n1, lda, n2, A, lda, n1, base));
+  GemmCall g{A + n1, A + n1, A + n1 + n1 * lda, lda, lda, lda, n2, n2, n1, -1.0, 1.0, false, false, true};
+  GPC_CHECK(launch_gemm(g, d.s, d.launches));
+  return potrf_rec(d, A + n1 + n1 * lda, lda, n2, base + n1);
+}
+
+// Out (n x n, full symmetric) = (L L')^-1 by the Schur-complement recursion:
+//   K^-1 = [A^-1 + X' S^-1 X, -X' S^-1; -S^-1 X, S^-1],  X = L21 L11^-1, S^-1 = (L22 L22')^-1
+int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo,
+                     int64_t dbase) {
+  if (n == TILE) {
+    const double* Di = d.Dinv + dbase * TILE;
+    GemmCall g{Di, Di, Out, TILE, TILE, ldo, TILE, TILE, TILE, 1.0, 0.0, true, true, false};
+    return launch_gemm(g, d.s, d.launches);
+  }
+  int64_t n1 = split(n), n2 = n - n1;
+  GPC_CHECK(potri_rec(d, L, ldl, n1, Out, ldo, dbase));
+  GPC_CHECK(potri_rec(d, L + n1 + n1 * ldl, ldl, n2, Out + n1 + n1 * ldo, ldo, dbase + n1));
+  double* X = d.W;  // n2 x n1, ld n2
+  GPC_CHECK(launch_copy_block(L + n1, ldl, X, n2, n2, n1, 1.0, d.s, d.launches));
+  GPC_CHECK(trsm_rln(d, X, n2, n2, L, ldl, n1, dbase));
+  {  // Out21 = -Out22 * X
+    GemmCall g{Out + n1 + n1 * ldo, X, Out + n1, ldo, n2, ldo, n2, n1, n2, -1.0, 0.0, false, true, false};
+    GPC_CHECK(launch_gemm(g, d.s, d.launches));
+  }
+  {  // Out11 -= X' * Out21 (lower), then mirror
+    GemmCall g{X, Out + n1, Out, n2, ldo, ldo, n1, n1, n2, -1.0, 1.0, true, true, true};
+    GPC_CHECK(launch_gemm(g, d.s, d.launches));
+    GPC_CHECK(launch_mirror_lower(Out, ldo, n1, d.s, d.launches));
+  }
+  return launch_transpose(Out + n1, ldo, Out + n1 * ldo, ldo, n2, n1, d.s, d.launches);
+}
+
+}  // namespace gpc
+
+using namespace gpc;
+
+// ------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------
+struct gpc_ctx {
+  int device;
+  cudaStream_t own_stream, stream;
+  int64_t Nmax, Npmax;
+  int Dmax, dmax;
+  int64_t N, Np;
+  int D, d;
+  double *X, *M, *alpha, *K, *L, *Kinv, *W, *Dinv;
+  double* scal;    // device scalars: [0] logdet [1] quad [2] trace ; then g[GPC_MAX_PARAMS]
+  int* info;       // device
+  double* partial; // grad partial sums
+  double* gXdev;
+  int max_ctas;
+  double* hres;    // pinned host result buffer
+  int* hinfo;      // pinned
+  bool haveX, haveM, haveK, haveL, haveInv, haveAlpha;
+  int64_t launches;
+  cudaEvent_t ev[6];
+  double last_ms[6];
+  // scratch for cross-covariances (grown on demand)
+  double *Xs, *Kc, *tmp1, *tmp2;
+  int64_t Xs_cap, Kc_cap, tmp_cap;
+};
+
+static const int SC_LOGDET = 0, SC_QUAD = 1, SC_TRACE = 2, SC_G = 8;
+
+static Dense dense_of(gpc_ctx* c) {
+  Dense d;
+  d.s = c->stream;
+  d.launches = &c->launches;
+  d.Dinv = c->Dinv;
+  d.info = c->info;
+  d.logdet = c->scal + SC_LOGDET;
+  d.W = c->W;
+  d.nvalid = c->N;
+  return d;
+}
+
+static int ensure_inverse_buffers(gpc_ctx* c) {
+  if (c->Kinv) return GPC_OK;
+  size_t nn = (size_t)c->Npmax * c->Npmax;
+  GPC_CUDA_CHECK(cudaMalloc(&c->Kinv, nn * sizeof(double)));
+  size_t h = (size_t)(c->Npmax / 2 + TILE);
+  GPC_CUDA_CHECK(cudaMalloc(&c->W, h * h * sizeof(double)));
+  return GPC_OK;
+}
+
+extern "C" {
+
+const char* gpc_last_error(void) { return g_error.c_str(); }
+
+int gpc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int gpc_kern_nparams(int type, int D) {
+  switch (type) {
+    case GPC_KERN_WHITE:
+    case GPC_KERN_BIAS:
+    case GPC_KERN_LIN: return 1;
+    case GPC_KERN_RBF:
+    case GPC_KERN_MATERN32:
+    case GPC_KERN_MATERN52: return 2;
+    case GPC_KERN_POLY: return 3;
+    case GPC_KERN_RBFARD: return 2 + D;
+  }
+  return -1;
+}
+int gpc_kern_transform(int type, int idx) {
+  if (type == GPC_KERN_RBFARD && idx >= 2) return GPC_TRANS_SIGMOID;  // CKern.cpp:3210-3217 defaultZeroOne
+  return GPC_TRANS_EXP;                                                // defaultPositive
+}
+static const double LIMVAL = 36.0;  // CTransform.h:17
+double gpc_transform_atox(int tr, double a) {
+  switch (tr) {
+    case GPC_TRANS_EXP:  // CTransform.cpp:31-42
+      if (a < -LIMVAL) return exp(-LIMVAL);
+      if (a < LIMVAL) return exp(a);
+      return exp(LIMVAL);
+    case GPC_TRANS_SIGMOID:  // CTransform.cpp:96-104
+      if (a < -LIMVAL) return 2.220446049250313e-16;
+      if (a < LIMVAL) return 1.0 / (1.0 + exp(-a));
+      return 1.0 - 2.220446049250313e-16;
+  }
+  return a;
+}
+double gpc_transform_xtoa(int tr, double x) {
+  switch (tr) {
+    case GPC_TRANS_EXP: return log(x);
+    case GPC_TRANS_SIGMOID: return log(x / (1.0 - x));
+  }
+  return x;
+}
+double gpc_transform_gradfact(int tr, double x) {
+  switch (tr) {
+    case GPC_TRANS_EXP: return x;
+    case GPC_TRANS_SIGMOID: return x * (1.0 - x);
+  }
+  return 1.0;
+}
+
+int gpc_ctx_create(gpc_ctx** out, int device, int64_t Nmax, int Dmax, int dout_max) {
+  if (!out || Nmax < 1 || Dmax < 1 || dout_max < 1) {
+    set_error("gpc_ctx_create: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  int ndev = 0;
+  GPC_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) {
+    set_error("gpc_ctx_create: no such CUDA device");
+    return GPC_ERR_CUDA;
+  }
+  GPC_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GPC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("gpc_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    return GPC_ERR_CUDA;
+  }
+  gpc_ctx* c = new gpc_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->Nmax = Nmax;
+  c->Npmax = round_up(Nmax, TILE);
+  c->Dmax = Dmax;
+  c->dmax = dout_max;
+  c->max_ctas = prop.multiProcessorCount * 2;
+  GPC_CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  size_t np = (size_t)c->Npmax;
+  GPC_CUDA_CHECK(cudaMalloc(&c->X, np * Dmax * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->M, np * dout_max * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->alpha, np * dout_max * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->K, np * np * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->L, np * np * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->Dinv, np * TILE * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->scal, (SC_G + GPC_MAX_PARAMS) * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->info, sizeof(int)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->partial, (size_t)c->max_ctas * GPC_MAX_PARAMS * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->gXdev, np * Dmax * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMallocHost(&c->hres, (SC_G + GPC_MAX_PARAMS) * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMallocHost(&c->hinfo, sizeof(int)));
+  GPC_CUDA_CHECK(cudaMemset(c->X, 0, np * Dmax * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMemset(c->M, 0, np * dout_max * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMemset(c->alpha, 0, np * dout_max * sizeof(double)));
+  for (int i = 0; i < 6; i++) GPC_CUDA_CHECK(cudaEventCreate(&c->ev[i]));
+  *out = c;
+  return GPC_OK;
+}
+
+int gpc_ctx_destroy(gpc_ctx* c) {
+  if (!c) return GPC_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->X); cudaFree(c->M); cudaFree(c->alpha); cudaFree(c->K); cudaFree(c->L);
+  cudaFree(c->Kinv); cudaFree(c->W); cudaFree(c->Dinv); cudaFree(c->scal); cudaFree(c->info);
+  cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->tmp1); cudaFree(c->tmp2);
+  cudaFreeHost(c->hres); cudaFreeHost(c->hinfo);
+  for (int i = 0; i < 6; i++) cudaEventDestroy(c->ev[i]);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+  return GPC_OK;
+}
+
+int gpc_ctx_set_stream(gpc_ctx* c, void* s) {
+  if (!c) return GPC_ERR_ARG;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return GPC_OK;
+}
+void* gpc_ctx_get_stream(gpc_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int gpc_ctx_sync(gpc_ctx* c) {
+  if (!c) return GPC_ERR_ARG;
+  GPC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return GPC_OK;
+}
+int64_t gpc_ctx_launch_count(gpc_ctx* c) { return c ? c->launches : 0; }
+
+static int upload(gpc_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
+  GPC_CUDA_CHECK(cudaMemcpy2DAsync(dst, ldd * sizeof(double), src, lds * sizeof(double), rows * sizeof(double), cols,
+                                   cudaMemcpyHostToDevice, c->stream));
+  return GPC_OK;
+}
+static int download(gpc_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows,
+                    int64_t cols) {
+  GPC_CUDA_CHECK(cudaMemcpy2DAsync(dst, ldd * sizeof(double), src, lds * sizeof(double), rows * sizeof(double), cols,
+                                   cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return GPC_OK;
+}
+
+int gpc_set_X(gpc_ctx* c, const double* X, int64_t N, int D, int64_t ldx) {
+  if (!c || !X || N < 1 || N > c->Nmax || D < 1 || D > c->Dmax || ldx < N) {
+    set_error("gpc_set_X: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  GPC_CUDA_CHECK(cudaSetDevice(c->device));
+  int64_t Np = round_up(N, TILE);
+  if (c->haveX && (Np != c->Np || N != c->N))  // stale rows beyond the new N must read as zero
+    GPC_CUDA_CHECK(cudaMemsetAsync(c->X, 0, (size_t)c->Npmax * c->Dmax * sizeof(double), c->stream));
+  c->N = N;
+  c->Np = Np;
+  c->D = D;
+  GPC_CHECK(upload(c, c->X, Np, X, ldx, N, D));
+  c->haveX = true;
+  c->haveK = c->haveL = c->haveInv = c->haveAlpha = false;
+  return GPC_OK;
+}
+
+int gpc_set_M(gpc_ctx* c, const double* M, int64_t N, int d, int64_t ldm) {
+  if (!c || !M || !c->haveX || N != c->N || d < 1 || d > c->dmax || ldm < N) {
+    set_error("gpc_set_M: bad arguments (set X first; N must match)");
+    return GPC_ERR_ARG;
+  }
+  GPC_CUDA_CHECK(cudaSetDevice(c->device));
+  GPC_CUDA_CHECK(cudaMemsetAsync(c->M, 0, (size_t)c->Npmax * c->dmax * sizeof(double), c->stream));
+  GPC_CUDA_CHECK(cudaMemsetAsync(c->alpha, 0, (size_t)c->Npmax * c->dmax * sizeof(double), c->stream));
+  c->d = d;
+  GPC_CHECK(upload(c, c->M, c->Np, M, ldm, N, d));
+  c->haveM = true;
+  c->haveAlpha = false;
+  return GPC_OK;
+}
+
+int gpc_set_Y(gpc_ctx* c, const double* Y, int64_t N, int d, int64_t ldy, const double* bias, const double* scale) {
+  // m(:,j) = (y(:,j) - bias_j) / scale_j  (CGp::updateM, CGp.cpp:248-260): O(N d) host work, then one upload
+  if (!c || !Y || N < 1 || d < 1 || ldy < N) {
+    set_error("gpc_set_Y: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  std::vector<double> m((size_t)N * d);
+  for (int j = 0; j < d; j++) {
+    double b = bias ? bias[j] : 0.0, inv = 1.0 / (scale ? scale[j] : 1.0);
+    for (int64_t i = 0; i < N; i++) m[i + (size_t)j * N] = (Y[i + (size_t)j * ldy] - b) * inv;
+  }
+  int rc = gpc_set_M(c, m.data(), N, d, N);
+  if (rc == GPC_OK) rc = gpc_ctx_sync(c);  // m is a temporary
+  return rc;
+}
+
+static int need(gpc_ctx* c, bool cond, const char* what) {
+  if (!c) {
+    set_error("null context");
+    return GPC_ERR_ARG;
+  }
+  if (!cond) {
+    set_error(std::string("state: ") + what);
+    return GPC_ERR_STATE;
+  }
+  if (cudaSetDevice(c->device) != cudaSuccess) {
+    set_error("cudaSetDevice failed");
+    return GPC_ERR_CUDA;
+  }
+  return GPC_OK;
+}
+
+int gpc_kern_build(gpc_ctx* c, const gpc_kcomp* comps, int ncomp) {
+  GPC_CHECK(need(c, c && c->haveX, "gpc_kern_build needs X"));
+  KSpec ks;
+  GPC_CHECK(make_kspec(comps, ncomp, c->D, &ks));
+  GPC_CHECK(launch_kbuild(ks, c->X, c->Np, c->N, c->Np, c->K, c->Np, c->stream, &c->launches));
+  c->haveK = true;
+  c->haveL = c->haveInv = c->haveAlpha = false;
+  return GPC_OK;
+}
+
+int gpc_add_diag(gpc_ctx* c, double jitter) {
+  GPC_CHECK(need(c, c && c->haveK, "gpc_add_diag needs K"));
+  GPC_CHECK(launch_add_diag(c->K, c->Np, c->N, jitter, c->stream, &c->launches));
+  c->haveL = c->haveInv = c->haveAlpha = false;
+  return GPC_OK;
+}
+
+static int potrf_async(gpc_ctx* c) {
+  GPC_CUDA_CHECK(cudaMemsetAsync(c->info, 0, sizeof(int), c->stream));
+  GPC_CUDA_CHECK(cudaMemsetAsync(c->scal + SC_LOGDET, 0, sizeof(double), c->stream));
+  GPC_CHECK(launch_copy_lower(c->K, c->Np, c->L, c->Np, c->Np, c->stream, &c->launches));
+  Dense d = dense_of(c);
+  return potrf_rec(d, c->L, c->Np, c->Np, 0);
+}
+
+int gpc_potrf(gpc_ctx* c, int* info, double* logdet) {
+  GPC_CHECK(need(c, c && c->haveK, "gpc_potrf needs K"));
+  GPC_CHECK(potrf_async(c));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(c->hinfo, c->info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (info) *info = *c->hinfo;
+  if (logdet) *logdet = c->hres[SC_LOGDET];
+  c->haveL = (*c->hinfo == 0);
+  c->haveInv = c->haveAlpha = false;
+  return *c->hinfo;
+}
+
+static int trace_K(gpc_ctx* c, double* tr) {
+  // trace via a strided dot with ones is overkill: download the diagonal (N doubles)
+  std::vector<double> diag((size_t)c->N);
+  GPC_CUDA_CHECK(cudaMemcpy2DAsync(diag.data(), sizeof(double), c->K, (c->Np + 1) * sizeof(double), sizeof(double),
+                                   c->N, cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  double t = 0.0;
+  for (int64_t i = 0; i < c->N; i++) t += diag[i];
+  *tr = t;
+  return GPC_OK;
+}
+
+int gpc_jitchol(gpc_ctx* c, int max_tries, double* jitter_out, double* logdet) {
+  GPC_CHECK(need(c, c && c->haveK, "gpc_jitchol needs K"));
+  if (max_tries <= 0) max_tries = 20;  // CMatrix.h:1060 default
+  double jitter = 0.0;
+  bool have_trace = false;
+  int tries = 0;
+  while (tries < max_tries) {
+    int info = 0;
+    int rc = gpc_potrf(c, &info, logdet);
+    if (rc < 0) return rc;
+    if (info == 0) {
+      if (!have_trace) {
+        double tr;
+        GPC_CHECK(trace_K(c, &tr));
+        jitter = 1e-6 * tr / (double)c->N;
+      }
+      if (jitter_out) *jitter_out = jitter;
+      return GPC_OK;
+    }
+    if (!have_trace) {
+      double tr;
+      GPC_CHECK(trace_K(c, &tr));
+      jitter = 1e-6 * tr / (double)c->N;  // CMatrix.cpp:775
+      have_trace = true;
+    }
+    GPC_CHECK(gpc_add_diag(c, jitter));  // A.addDiag(jitter) mutates K (CMatrix.cpp:787)
+    jitter *= 10.0;
+    tries++;
+    if (jitter > 10.0) {  // CMatrix.cpp:790-791
+      if (jitter_out) *jitter_out = jitter;
+      set_error("jitChol: matrix is non positive definite (jitter > 10)");
+      return info;
+    }
+  }
+  if (jitter_out) *jitter_out = jitter;
+  set_error("jitChol: adding jitter failed after max tries");
+  return 1;
+}
+
+int gpc_inverse(gpc_ctx* c) {
+  GPC_CHECK(need(c, c && c->haveL, "gpc_inverse needs a successful gpc_potrf"));
+  GPC_CHECK(ensure_inverse_buffers(c));
+  Dense d = dense_of(c);
+  GPC_CHECK(potri_rec(d, c->L, c->Np, c->Np, c->Kinv, c->Np, 0));
+  c->haveInv = true;
+  return GPC_OK;
+}
+
+static int alpha_from_inverse_async(gpc_ctx* c) {
+  GPC_CUDA_CHECK(cudaMemsetAsync(c->scal + SC_QUAD, 0, sizeof(double), c->stream));
+  GPC_CHECK(launch_symm_small(c->Kinv, c->Np, c->M, c->Np, c->alpha, c->Np, c->N, c->d, nullptr, c->stream,
+                              &c->launches));
+  return launch_dot(c->M, c->alpha, c->Np * c->d, c->scal + SC_QUAD, c->stream, &c->launches);
+}
+
+int gpc_alpha_from_inverse(gpc_ctx* c, double* quad) {
+  GPC_CHECK(need(c, c && c->haveInv && c->haveM, "gpc_alpha_from_inverse needs K^-1 and m"));
+  GPC_CHECK(alpha_from_inverse_async(c));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres, c->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (quad) *quad = c->hres[SC_QUAD];
+  c->haveAlpha = true;
+  return GPC_OK;
+}
+
+static int ensure_tmp(gpc_ctx* c, int64_t elems) {
+  if (c->tmp_cap >= elems) return GPC_OK;
+  cudaFree(c->tmp1);
+  cudaFree(c->tmp2);
+  c->tmp1 = c->tmp2 = nullptr;
+  c->tmp_cap = 0;
+  GPC_CUDA_CHECK(cudaMalloc(&c->tmp1, (size_t)elems * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->tmp2, (size_t)elems * sizeof(double)));
+  c->tmp_cap = elems;
+  return GPC_OK;
+}
+
+// alpha = L^-T L^-1 m through the triangular factor: work on the transposed right-hand side (dp x Np),
+// dp = TILE-padded output count, so that both solves are right-sided: Z L' = M', then A L = Z.
+int gpc_solve_alpha(gpc_ctx* c, double* quad) {
+  GPC_CHECK(need(c, c && c->haveL && c->haveM, "gpc_solve_alpha needs L and m"));
+  int64_t dp = round_up(c->d, TILE);
+  GPC_CHECK(ensure_tmp(c, dp * c->Np));
+  Dense d = dense_of(c);
+  GPC_CUDA_CHECK(cudaMemsetAsync(c->tmp1, 0, (size_t)dp * c->Np * sizeof(double), c->stream));
+  GPC_CHECK(launch_transpose(c->M, c->Np, c->tmp1, dp, c->Np, c->d, c->stream, &c->launches));
+  GPC_CHECK(trsm_rlt(d, c->tmp1, dp, dp, c->L, c->Np, c->Np, 0));
+  GPC_CHECK(trsm_rln(d, c->tmp1, dp, dp, c->L, c->Np, c->Np, 0));
+  GPC_CHECK(launch_transpose(c->tmp1, dp, c->alpha, c->Np, c->d, c->Np, c->stream, &c->launches));
+  GPC_CUDA_CHECK(cudaMemsetAsync(c->scal + SC_QUAD, 0, sizeof(double), c->stream));
+  GPC_CHECK(launch_dot(c->M, c->alpha, c->Np * c->d, c->scal + SC_QUAD, c->stream, &c->launches));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres, c->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (quad) *quad = c->hres[SC_QUAD];
+  c->haveAlpha = true;
+  return GPC_OK;
+}
+
+static int grad_async(gpc_ctx* c, const KSpec& ks, bool wantX) {
+  if (wantX) GPC_CUDA_CHECK(cudaMemsetAsync(c->gXdev, 0, (size_t)c->Np * c->D * sizeof(double), c->stream));
+  return launch_grad(ks, c->X, c->Np, c->N, c->Np, c->Kinv, c->Np, c->alpha, c->Np, c->d, 0, c->partial, c->max_ctas,
+                     c->scal + SC_G, wantX ? c->gXdev : nullptr, c->Np, c->stream, &c->launches);
+}
+
+int gpc_grad(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, double* gparams, double* gX) {
+  GPC_CHECK(need(c, c && c->haveInv && c->haveAlpha, "gpc_grad needs K^-1 and alpha"));
+  KSpec ks;
+  GPC_CHECK(make_kspec(comps, ncomp, c->D, &ks));
+  GPC_CHECK(grad_async(c, ks, gX != nullptr));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres + SC_G, c->scal + SC_G, ks.nparams * sizeof(double), cudaMemcpyDeviceToHost,
+                                 c->stream));
+  if (gX) GPC_CHECK(download(c, gX, c->N, c->gXdev, c->Np, c->N, c->D));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < ks.nparams; i++) gparams[i] = c->hres[SC_G + i];
+  return GPC_OK;
+}
+
+int gpc_kern_grad(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* covGrad, int64_t ldc, double* gparams,
+                  double* gX) {
+  GPC_CHECK(need(c, c && c->haveX, "gpc_kern_grad needs X"));
+  if (!covGrad || ldc < c->N) {
+    set_error("gpc_kern_grad: bad covGrad");
+    return GPC_ERR_ARG;
+  }
+  KSpec ks;
+  GPC_CHECK(make_kspec(comps, ncomp, c->D, &ks));
+  GPC_CHECK(ensure_inverse_buffers(c));
+  // stage covGrad in the K^-1 buffer (invalidates it)
+  c->haveInv = false;
+  GPC_CHECK(upload(c, c->Kinv, c->Np, covGrad, ldc, c->N, c->N));
+  if (gX) GPC_CUDA_CHECK(cudaMemsetAsync(c->gXdev, 0, (size_t)c->Np * c->D * sizeof(double), c->stream));
+  GPC_CHECK(launch_grad(ks, c->X, c->Np, c->N, c->Np, c->Kinv, c->Np, nullptr, 0, 0, 1, c->partial, c->max_ctas,
+                        c->scal + SC_G, gX ? c->gXdev : nullptr, c->Np, c->stream, &c->launches));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres + SC_G, c->scal + SC_G, ks.nparams * sizeof(double), cudaMemcpyDeviceToHost,
+                                 c->stream));
+  if (gX) GPC_CHECK(download(c, gX, c->N, c->gXdev, c->Np, c->N, c->D));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < ks.nparams; i++) gparams[i] = c->hres[SC_G + i];
+  return GPC_OK;
+}
+
+static int ensure_cross(gpc_ctx* c, int64_t Nsp) {
+  if (c->Xs_cap < Nsp * c->Dmax) {
+    cudaFree(c->Xs);
+    c->Xs = nullptr;
+    GPC_CUDA_CHECK(cudaMalloc(&c->Xs, (size_t)Nsp * c->Dmax * sizeof(double)));
+    c->Xs_cap = Nsp * c->Dmax;
+  }
+  if (c->Kc_cap < Nsp * c->Np) {
+    cudaFree(c->Kc);
+    c->Kc = nullptr;
+    GPC_CUDA_CHECK(cudaMalloc(&c->Kc, (size_t)Nsp * c->Np * sizeof(double)));
+    c->Kc_cap = Nsp * c->Np;
+  }
+  return GPC_OK;
+}
+
+int gpc_kern_cross(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* Xs, int64_t Ns, int64_t ldxs,
+                   double* Ks, int64_t ldk) {
+  GPC_CHECK(need(c, c && c->haveX, "gpc_kern_cross needs X"));
+  if (!Xs || !Ks || Ns < 1 || ldxs < Ns || ldk < c->N) {
+    set_error("gpc_kern_cross: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  KSpec ks;
+  GPC_CHECK(make_kspec(comps, ncomp, c->D, &ks));
+  int64_t Nsp = round_up(Ns, TILE);
+  GPC_CHECK(ensure_cross(c, Nsp));
+  GPC_CHECK(upload(c, c->Xs, Nsp, Xs, ldxs, Ns, c->D));
+  GPC_CHECK(launch_kcross(ks, c->X, c->Np, c->N, c->Np, c->Xs, Nsp, Ns, Nsp, c->Kc, c->Np, c->stream, &c->launches));
+  return download(c, Ks, ldk, c->Kc, c->Np, c->N, Ns);
+}
+
+int gpc_kern_diag(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* Xs, int64_t Ns, int64_t ldxs,
+                  double* kdiag) {
+  GPC_CHECK(need(c, c != nullptr, "ctx"));
+  if (!Xs || !kdiag || Ns < 1 || ldxs < Ns || !c->haveX) {
+    set_error("gpc_kern_diag: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  KSpec ks;
+  GPC_CHECK(make_kspec(comps, ncomp, c->D, &ks));
+  int64_t Nsp = round_up(Ns, TILE);
+  GPC_CHECK(ensure_cross(c, Nsp));
+  GPC_CHECK(ensure_tmp(c, Nsp));
+  GPC_CHECK(upload(c, c->Xs, Nsp, Xs, ldxs, Ns, c->D));
+  GPC_CHECK(launch_kdiag(ks, c->Xs, Nsp, Ns, c->tmp1, c->stream, &c->launches));
+  return download(c, kdiag, Ns, c->tmp1, Nsp, Ns, 1);
+}
+
+int gpc_posterior(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* Xs, int64_t Ns, int64_t ldxs,
+                  double* mu, double* var) {
+  GPC_CHECK(need(c, c && c->haveL && c->haveAlpha, "gpc_posterior needs L and alpha"));
+  if (!Xs || !mu || Ns < 1 || ldxs < Ns) {
+    set_error("gpc_posterior: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  KSpec ks;
+  GPC_CHECK(make_kspec(comps, ncomp, c->D, &ks));
+  int64_t Nsp = round_up(Ns, TILE);
+  GPC_CHECK(ensure_cross(c, Nsp));
+  GPC_CHECK(ensure_tmp(c, Nsp * (c->d > 1 ? c->d : 1) + Nsp));
+  GPC_CHECK(upload(c, c->Xs, Nsp, Xs, ldxs, Ns, c->D));
+  // Kc = K(Xs, X): Nsp x Np, test points along rows so that the solve is right-sided: V L' = Kc
+  GPC_CHECK(launch_kcross(ks, c->Xs, Nsp, Ns, Nsp, c->X, c->Np, c->N, c->Np, c->Kc, Nsp, c->stream, &c->launches));
+  // mu = Kc alpha  (CGp::_posteriorMean, CGp.cpp:548-560)
+  GPC_CHECK(launch_gemv_rows(c->Kc, Nsp, Ns, c->N, c->alpha, c->Np, c->d, c->tmp1, Nsp, c->stream, &c->launches));
+  GPC_CHECK(download(c, mu, Ns, c->tmp1, Nsp, Ns, c->d));
+  if (var) {
+    // var = k(x*,x*) - |L^-1 k*|^2  (CGp::_posteriorVar FTC, CGp.cpp:600-613)
+    Dense d = dense_of(c);
+    GPC_CHECK(trsm_rlt(d, c->Kc, Nsp, Nsp, c->L, c->Np, c->Np, 0));
+    GPC_CHECK(launch_kdiag(ks, c->Xs, Nsp, Ns, c->tmp2, c->stream, &c->launches));
+    GPC_CHECK(launch_row_sqnorm_sub(c->Kc, Nsp, Ns, c->N, c->tmp2, c->tmp1, c->stream, &c->launches));
+    std::vector<double> v((size_t)Ns);
+    GPC_CHECK(download(c, v.data(), Ns, c->tmp1, Nsp, Ns, 1));
+    for (int j = 0; j < c->d; j++)  // same variance for every output (CGp.cpp:608-611)
+      memcpy(var + (size_t)j * Ns, v.data(), sizeof(double) * Ns);
+  }
+  return GPC_OK;
+}
+
+int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* out, double* gparams, double* gX) {
+  GPC_CHECK(need(c, c && c->haveX && c->haveM, "gpc_eval needs X and m"));
+  KSpec ks;
+  GPC_CHECK(make_kspec(comps, ncomp, c->D, &ks));
+  GPC_CHECK(ensure_inverse_buffers(c));
+  bool wantX = (flags & 1) && gX;
+  Dense d = dense_of(c);
+  cudaStream_t s = c->stream;
+  GPC_CUDA_CHECK(cudaEventRecord(c->ev[0], s));
+  GPC_CHECK(launch_kbuild(ks, c->X, c->Np, c->N, c->Np, c->K, c->Np, s, &c->launches));
+  c->haveK = true;
+  GPC_CUDA_CHECK(cudaEventRecord(c->ev[1], s));
+  double jitter_used = 0.0;
+  double jitter = 0.0;
+  bool have_trace = false;
+  for (int tries = 0;; tries++) {
+    GPC_CHECK(potrf_async(c));
+    GPC_CUDA_CHECK(cudaEventRecord(c->ev[2], s));
+    // optimistic: queue the rest before looking at info (a failed factorisation is rare and just redone)
+    GPC_CHECK(potri_rec(d, c->L, c->Np, c->Np, c->Kinv, c->Np, 0));
+    GPC_CUDA_CHECK(cudaEventRecord(c->ev[3], s));
+    GPC_CHECK(alpha_from_inverse_async(c));
+    GPC_CUDA_CHECK(cudaEventRecord(c->ev[4], s));
+    GPC_CHECK(grad_async(c, ks, wantX));
+    GPC_CUDA_CHECK(cudaEventRecord(c->ev[5], s));
+    GPC_CUDA_CHECK(cudaMemcpyAsync(c->hinfo, c->info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres, c->scal, (SC_G + ks.nparams) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GPC_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (*c->hinfo == 0) break;
+    // jitChol schedule (CMatrix.cpp:767-804)
+    if (!have_trace) {
+      double tr;
+      GPC_CHECK(trace_K(c, &tr));
+      jitter = 1e-6 * tr / (double)c->N;
+      have_trace = true;
+    }
+    GPC_CHECK(launch_add_diag(c->K, c->Np, c->N, jitter, s, &c->launches));
+    jitter_used += jitter;
+    jitter *= 10.0;
+    if (jitter > 10.0 || tries + 1 >= 20) {
+      set_error("gpc_eval: kernel matrix is non positive definite after jitter retries");
+      return *c->hinfo;
+    }
+  }
+  c->haveL = c->haveInv = c->haveAlpha = true;
+  if (out) {
+    out[0] = c->hres[SC_LOGDET];
+    out[1] = c->hres[SC_QUAD];
+    out[2] = jitter_used;
+  }
+  if (gparams)
+    for (int i = 0; i < ks.nparams; i++) gparams[i] = c->hres[SC_G + i];
+  if (wantX) GPC_CHECK(download(c, gX, c->N, c->gXdev, c->Np, c->N, c->D));
+  for (int i = 0; i < 5; i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
+    c->last_ms[i] = ms;
+  }
+  float tot = 0.f;
+  cudaEventElapsedTime(&tot, c->ev[0], c->ev[5]);
+  c->last_ms[5] = tot;
+  return GPC_OK;
+}
+
+int gpc_last_timings(gpc_ctx* c, double* ms6) {
+  if (!c || !ms6) return GPC_ERR_ARG;
+  for (int i = 0; i < 6; i++) ms6[i] = c->last_ms[i];
+  return GPC_OK;
+}
+
+int gpc_download(gpc_ctx* c, int which, double* dst, int64_t ld) {
+  GPC_CHECK(need(c, c && dst, "gpc_download"));
+  int64_t N = c->N;
+  switch (which) {
+    case GPC_MAT_K:
+      GPC_CHECK(need(c, c->haveK, "K not built"));
+      GPC_CHECK(download(c, dst, ld, c->K, c->Np, N, N));
+      for (int64_t j = 0; j < N; j++)
+        for (int64_t i = 0; i < j; i++) dst[i + j * ld] = dst[j + i * ld];  // device keeps the lower triangle
+      return GPC_OK;
+    case GPC_MAT_L:
+      GPC_CHECK(need(c, c->haveL, "L not available"));
+      GPC_CHECK(download(c, dst, ld, c->L, c->Np, N, N));
+      for (int64_t j = 0; j < N; j++)
+        for (int64_t i = 0; i < j; i++) dst[i + j * ld] = 0.0;
+      return GPC_OK;
+    case GPC_MAT_KINV:
+      GPC_CHECK(need(c, c->haveInv, "K^-1 not available"));
+      return download(c, dst, ld, c->Kinv, c->Np, N, N);
+    case GPC_MAT_ALPHA:
+      GPC_CHECK(need(c, c->haveAlpha, "alpha not available"));
+      return download(c, dst, ld, c->alpha, c->Np, N, c->d);
+    case GPC_MAT_M:
+      GPC_CHECK(need(c, c->haveM, "m not set"));
+      return download(c, dst, ld, c->M, c->Np, N, c->d);
+  }
+  set_error("gpc_download: unknown matrix");
+  return GPC_ERR_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// common.cuh -- shared declarations for libgpc_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/gpc_b200.h"
+
+namespace gpc {
+
+constexpr int TILE = 128;  // every device matrix is padded to a multiple of TILE in both dimensions
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+void set_error(const std::string& s);
+#define GPC_CUDA_CHECK(expr)                                                                        \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      gpc::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" +    \
+                     std::to_string(__LINE__));                                                     \
+      return GPC_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+
+// ---- kernel specification passed by value to the K-build / gradient kernels --------------------------
+struct KSpec {
+  int ncomp;
+  int D;
+  int nparams;                    // total
+  int need_r2, need_dot;          // which pair quantities any component consumes
+  int type[GPC_MAX_COMPONENTS];
+  int poff[GPC_MAX_COMPONENTS];   // offset of the component's first parameter in p[]
+  double degree[GPC_MAX_COMPONENTS];
+  double p[GPC_MAX_PARAMS];
+};
+int make_kspec(const gpc_kcomp* comps, int ncomp, int D, KSpec* out);
+
+// ---- dense layer (dense.cu) ---------------------------------------------------------------------------
+// C(m x n) = alpha * opA(A)(m x k) * opB(B)(k x n) + beta * C.   All dims multiples of TILE (k of 16).
+//   a_kc: A is stored with k contiguous, i.e. opA(A)(i,kk) = A[kk + i*lda]   ('T' in BLAS terms)
+//         otherwise                           opA(A)(i,kk) = A[i + kk*lda]   ('N')
+//   b_kc: B is stored with k contiguous, i.e. opB(B)(kk,j) = B[kk + j*ldb]   ('N' in BLAS terms)
+//         otherwise                           opB(B)(kk,j) = B[j + kk*ldb]   ('T')
+//   lower: only output tiles that intersect the lower triangle are computed (m == n required)
+struct GemmCall {
+  const double* A;
+  const double* B;
+  double* C;
+  int64_t lda, ldb, ldc;
+  int64_t m, n, k;
+  double alpha, beta;
+  bool a_kc, b_kc, lower;
+};
+int launch_gemm(const GemmCall& g, cudaStream_t s, int64_t* launches);
+
+// potrf of one TILE x TILE diagonal block, in place (lower); also writes the inverse of the factor into
+// Dinv (TILE x TILE, ld TILE, upper part zero), adds 2*sum(log diag) to *logdet and records the first
+// non-positive pivot (1-based global order = base + j + 1) in *info if *info == 0.
+int launch_potrf_leaf(double* A, int64_t lda, double* Dinv, int* info, int base, int64_t nvalid, double* logdet,
+                      cudaStream_t s, int64_t* launches);
+// misc elementwise / reductions
+int launch_copy_lower(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t n, cudaStream_t s,
+                      int64_t* launches);                       // dst lower(+diag) = src lower
+int launch_mirror_lower(double* A, int64_t lda, int64_t n, cudaStream_t s, int64_t* launches);  // upper := lower'
+int launch_copy_block(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t m, int64_t n, double scale,
+                      cudaStream_t s, int64_t* launches);
+int launch_transpose(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t m, int64_t n, cudaStream_t s,
+                     int64_t* launches);                        // dst(n x m) = src(m x n)'
+int launch_add_diag(double* A, int64_t lda, int64_t n, double v, cudaStream_t s, int64_t* launches);
+int launch_zero_upper(double* A, int64_t lda, int64_t n, cudaStream_t s, int64_t* launches);
+int launch_set_identity_pad(double* A, int64_t lda, int64_t n, int64_t np, cudaStream_t s, int64_t* launches);
+// y(n x d) = A(n x n, full) * x(n x d) ; also *dot += sum(x .* y)
+int launch_symm_small(const double* A, int64_t lda, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
+                      int d, double* dot, cudaStream_t s, int64_t* launches);
+int launch_dot(const double* x, const double* y, int64_t n, double* out, cudaStream_t s, int64_t* launches);
+
+// inverse of the lower-triangular TILE x TILE block at A (no factorisation): Dinv as above
+int launch_trtri_leaf(const double* A, int64_t lda, double* Dinv, cudaStream_t s, int64_t* launches);
+
+// ---- recursive blocked algorithms (api.cu) ---------------------------------------------------------------
+struct Dense {
+  cudaStream_t s;
+  int64_t* launches;
+  double* Dinv;    // n_total x TILE : inverse of diagonal block b at Dinv + b*TILE*TILE
+  int* info;       // device
+  double* logdet;  // device
+  double* W;       // workspace for the inverse (>= (n/2 + TILE)^2 doubles)
+  int64_t nvalid;  // rows below this index are real data (identity padding beyond)
+};
+int trsm_rlt(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n, int64_t dbase);
+int trsm_rln(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n, int64_t dbase);
+int potrf_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base);
+int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, int64_t dbase);
+
+// ---- GP layer (gpkern.cu) -----------------------------------------------------------------------------
+// K (np x np, ld ldk): lower-triangle tiles of the kernel matrix of X (n valid rows, padded part = identity)
+int launch_kbuild(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, double* K, int64_t ldk,
+                  cudaStream_t s, int64_t* launches);
+// Kc (n1p x n2p, ld ldk) = k(X1_i, X2_j) (computeElement semantics: white = 0), zero in the padding
+int launch_kcross(const KSpec& ks, const double* X1, int64_t ldx1, int64_t n1, int64_t n1p, const double* X2,
+                  int64_t ldx2, int64_t n2, int64_t n2p, double* Kc, int64_t ldk, cudaStream_t s, int64_t* launches);
+int launch_kdiag(const KSpec& ks, const double* X, int64_t ldx, int64_t n, double* out, cudaStream_t s,
+                 int64_t* launches);
+// gradient pass.  mode 0: covGrad = -1/2 (dout*Kinv - alpha alpha')   (Kinv lower triangle read only)
+//                 mode 1: covGrad = Cg (caller supplied, symmetric; lower triangle read only)
+// partial (gridDim x nparams) receives per-CTA sums, reduced by launch_reduce_partials into g (nparams).
+// gX (n x D, ld ldgx) accumulated with atomics when non-null (must be zeroed by the caller).
+int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, const double* Cg, int64_t ldc,
+                const double* alpha, int64_t lda, int dout, int mode, double* partial, int max_ctas, double* g,
+                double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches);
+// out[i] -= / = helpers for the posterior
+int launch_row_sqnorm_sub(const double* V, int64_t ldv, int64_t rows, int64_t cols, const double* kdiag, double* var,
+                          cudaStream_t s, int64_t* launches);  // var[i] = kdiag[i] - sum_j V[i,j]^2
+int launch_gemv_rows(const double* A, int64_t lda, int64_t rows, int64_t cols, const double* x, int64_t ldx, int d,
+                     double* y, int64_t ldy, cudaStream_t s, int64_t* launches);  // y(rows x d) = A(rows x cols) x
+
+}  // namespace gpc

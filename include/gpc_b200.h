@@ -1,0 +1,177 @@
+/* gpc_b200.h -- C ABI of libgpc_b200.so: the B200 (sm_100a) implementation of GPc's exact-GP hot path.
+ *
+ * The reference (SheffieldML/GPc) has no C ABI of its own: its seams are (1) the Fortran BLAS/LAPACK
+ * symbols declared in lapack.h:17-232 and (2) the C++ classes CMatrix / CKern / CGp / CGplvm.  This header
+ * is what a maintainer binds behind those classes; every entry point cites the
+ * reference code it replaces.  Conventions:
+ *   - plain pointers and sizes only; all matrices column-major fp64 exactly like CMatrix (CMatrix.h:268);
+ *   - pointers are HOST pointers unless the name ends in _dev;
+ *   - return value: 0 ok; >0 LAPACK-style numerical info (order of the first non-positive pivot, as
+ *     dpotrf_'s info, CMatrix.cpp:375-378); <0 usage / CUDA error, text via gpc_last_error();
+ *   - no C++ exception crosses this boundary; the C++ shim turns info>0 into ndlexceptions::MatrixNonPosDef;
+ *   - a gpc_ctx is single-threaded like a CGp object (mutable caches, CGp.h:365-447); several contexts on
+ *     different threads / devices are fine.
+ * There is NO CPU fallback: every call fails with GPC_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef GPC_B200_H
+#define GPC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden: only this ABI is exported */
+#endif
+
+#define GPC_OK 0
+#define GPC_ERR_ARG (-1)
+#define GPC_ERR_CUDA (-2)
+#define GPC_ERR_STATE (-3)
+#define GPC_ERR_NOMEM (-4)
+
+/* Kernel component types in scope.  Parameter order per component is the reference's:
+ *   WHITE    [variance]                              CKern.cpp:604-739
+ *   BIAS     [variance]                              CKern.cpp:889-1024
+ *   RBF      [inverseWidth, variance]                CKern.cpp:1028-1256
+ *   RBFARD   [inverseWidth, variance, scale_1..D]    CKern.cpp:3158-3417
+ *   MATERN32 [lengthScale, variance]                 CKern.cpp:1708-1952
+ *   MATERN52 [lengthScale, variance]                 CKern.cpp:1955-2216
+ *   LIN      [variance]                              CKern.cpp:2220-2383
+ *   POLY     [weightVariance, biasVariance, variance] (+ fixed degree)   CKern.cpp:2641-2905
+ * A list of components is CCmpndKern's sum (CKern.cpp:128-328). */
+enum gpc_kern_type {
+  GPC_KERN_WHITE = 0,
+  GPC_KERN_BIAS = 1,
+  GPC_KERN_RBF = 2,
+  GPC_KERN_RBFARD = 3,
+  GPC_KERN_MATERN32 = 4,
+  GPC_KERN_MATERN52 = 5,
+  GPC_KERN_LIN = 6,
+  GPC_KERN_POLY = 7
+};
+#define GPC_MAX_COMPONENTS 16
+#define GPC_MAX_PARAMS 288
+
+typedef struct gpc_kcomp {
+  int type;             /* gpc_kern_type */
+  int nparams;          /* must equal gpc_kern_nparams(type, D) */
+  const double* params; /* NATURAL (untransformed) values, reference order */
+  double degree;        /* POLY only (CPolyKern::degree, default 2) */
+} gpc_kcomp;
+
+/* transforms (CTransform.cpp:25-53 exp with +-36 clamp, :90-112 sigmoid with [eps,1-eps] clamp) */
+enum gpc_transform { GPC_TRANS_NONE = 0, GPC_TRANS_EXP = 1, GPC_TRANS_SIGMOID = 2 };
+int gpc_kern_nparams(int type, int D);
+int gpc_kern_transform(int type, int param_index); /* which transform the reference attaches to this parameter */
+double gpc_transform_atox(int transform, double a);
+double gpc_transform_xtoa(int transform, double x);
+double gpc_transform_gradfact(int transform, double x);
+
+typedef struct gpc_ctx gpc_ctx;
+
+const char* gpc_last_error(void);
+int gpc_device_count(void);
+
+/* ---- context: device-resident state of one CGp / CGplvm object --------------------------------------
+ * Owns X (N x D), m (N x d), K, L (= LcholK, lower), K^-1 (= invK), alpha; replaces the four N^2 host
+ * matrices CGp::initStoreage allocates (CGp.cpp:171-175, 178-246). */
+int gpc_ctx_create(gpc_ctx** out, int device, int64_t Nmax, int Dmax, int dout_max);
+int gpc_ctx_destroy(gpc_ctx* ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the context's own stream */
+int gpc_ctx_set_stream(gpc_ctx* ctx, void* cuda_stream);
+void* gpc_ctx_get_stream(gpc_ctx* ctx);
+int gpc_ctx_sync(gpc_ctx* ctx);
+/* number of kernel launches issued through this context since creation (bench.py's gpu_launches) */
+int64_t gpc_ctx_launch_count(gpc_ctx* ctx);
+
+/* X := host N x D (pX of CGp, CGp.h:353); M := host N x d, M = (y - bias)/scale i.e. CGp::updateM
+ * (CGp.cpp:248-260) is done by the caller, or use gpc_set_Y to do it on the device. */
+int gpc_set_X(gpc_ctx* ctx, const double* X, int64_t N, int D, int64_t ldx);
+int gpc_set_M(gpc_ctx* ctx, const double* M, int64_t N, int d, int64_t ldm);
+int gpc_set_Y(gpc_ctx* ctx, const double* Y, int64_t N, int d, int64_t ldy, const double* bias, const double* scale);
+
+/* K := kernel matrix of X.  Replaces CGp::_updateK FTC (CGp.cpp:693-712) / CKern::compute(K,X) (CKern.h:128-144):
+ * off-diagonal computeElement, diagonal diagComputeElement (white noise enters here only). */
+int gpc_kern_build(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp);
+/* K(X, Xs) -> host Ks (N x Ns, ld ldk).  Replaces CKern::compute(K,X,X2) (CKern.h:146-157); white contributes 0. */
+int gpc_kern_cross(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, const double* Xs, int64_t Ns, int64_t ldxs,
+                   double* Ks, int64_t ldk);
+/* diag k(Xs_i, Xs_i) -> host (CKern::diagCompute, CKern.h:50-56) */
+int gpc_kern_diag(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, const double* Xs, int64_t Ns, int64_t ldxs,
+                  double* kdiag);
+/* K += jitter * I   (CMatrix::addDiag as used by jitChol, CMatrix.cpp:787) */
+int gpc_add_diag(gpc_ctx* ctx, double jitter);
+/* L := chol(K) lower, logdet = 2 sum log L_ii.  Replaces LcholK.chol()/potrf (CMatrix.cpp:371-403, dpotrf_
+ * lapack.h:59-65) + logDet (CMatrix.cpp:404-412) + the zero-lower / Alg.513 transpose (CMatrix.cpp:391-395,
+ * CGp.cpp:890).  *info: 0 or the 1-based order of the first non-positive pivot (returned value is the same). */
+int gpc_potrf(gpc_ctx* ctx, int* info, double* logdet);
+/* jitChol (CMatrix.cpp:767-804) on the device-resident K: same jitter schedule, K mutated the same way.
+ * *jitter receives the value the reference returns. Returns >0 (info) if it gives up like the reference does. */
+int gpc_jitchol(gpc_ctx* ctx, int max_tries, double* jitter, double* logdet);
+/* alpha := L^-T L^-1 m (CGp::updateAlpha, CGp.cpp:469-484); *quad = sum_j m_j' alpha_j */
+int gpc_solve_alpha(gpc_ctx* ctx, double* quad);
+/* K^-1 from L (CMatrix::pdinv, CMatrix.cpp:421-432, dpotri_ lapack.h:67-73), full symmetric on the device */
+int gpc_inverse(gpc_ctx* ctx);
+/* alpha := K^-1 m via the explicit inverse (dsymv_, as CGp::logLikelihood does, CGp.cpp:924-930) */
+int gpc_alpha_from_inverse(gpc_ctx* ctx, double* quad);
+/* gparams[P] = sum_j sum_ik covGrad_j[i,k] dK[i,k]/dtheta, covGrad_j = -1/2 (K^-1 - alpha_j alpha_j')
+ * (CGp::updateCovGradient CGp.cpp:666-679 + CKern::getGradParams, e.g. CKern.cpp:1204-1241) WITHOUT ever
+ * materialising covGrad.  NATURAL-parameter gradients, component order; multiply by gpc_transform_gradfact for
+ * getGradTransParams (CKern.cpp:50-63).  gX (N x D, ld N) optional: d ll / d X as CGplvm accumulates it
+ * (CGplvm.cpp:569-603), without the latent prior term.  Needs gpc_inverse + an alpha. */
+int gpc_grad(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, double* gparams, double* gX);
+/* generic sum_ik covGrad[i,k] dK[i,k]/dtheta for a caller-supplied HOST covGrad (N x N, symmetric):
+ * CKern::getGradParams(g, X, covGrad) (CKern.h:187-197 and overrides) -- used by the kernel unit tests */
+int gpc_kern_grad(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, const double* covGrad, int64_t ldc,
+                  double* gparams, double* gX);
+/* posterior at Xs (Ns x D): mu (Ns x d, ld Ns), var (Ns x d, ld Ns) in the space of m (caller applies
+ * scale/bias, CGp.cpp:561-573, 622).  Replaces CGp::posteriorMeanVar (CGp.cpp:642-663): K(X,Xs) build,
+ * mu = K*' alpha, var = k(x*,x*) - |L^-1 k*|^2 (dtrsm_, CGp.cpp:603-606).  var may be NULL. */
+int gpc_posterior(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, const double* Xs, int64_t Ns, int64_t ldxs,
+                  double* mu, double* var);
+
+/* One full evaluation = what one SCG step asks of CGp (COptimisable.cpp:309-349):
+ * K build -> jitChol -> K^-1 -> alpha -> ll terms -> gradient.  out[0]=logdet, out[1]=quad, out[2]=jitter used.
+ * flags: bit0 = also compute gX (needs gX != NULL). Single host sync at the end. */
+int gpc_eval(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, int flags, double* out, double* gparams, double* gX);
+
+enum gpc_which { GPC_MAT_K = 0, GPC_MAT_L = 1, GPC_MAT_KINV = 2, GPC_MAT_ALPHA = 3, GPC_MAT_M = 4 };
+/* copy a device-resident matrix to the host (N x N or N x d).  K and K^-1 come back full symmetric, L lower
+ * with a zero strict upper triangle (LcholK after .trans(), CGp.cpp:890). */
+int gpc_download(gpc_ctx* ctx, int which, double* dst, int64_t ld);
+/* phase timings of the last gpc_eval in milliseconds (CUDA events on the context's stream):
+ * [0] K build [1] potrf [2] inverse [3] alpha+reductions [4] gradient [5] total */
+int gpc_last_timings(gpc_ctx* ctx, double* ms6);
+
+/* ---- CMatrix level: drop-ins for the lapack.h calls CMatrix makes (host pointers, LAPACK argument meaning,
+ *      scalars by value, 64-bit dimensions).  Each stages through device memory. ---------------------------*/
+/* dpotrf_ (lapack.h:59-65; CMatrix::potrf CMatrix.cpp:371-379) */
+int gpc_dpotrf(int device, char uplo, int64_t n, double* A, int64_t lda, int* info);
+/* dpotri_ (lapack.h:67-73; CMatrix::potri CMatrix.cpp:414-420): only the `uplo` triangle is written */
+int gpc_dpotri(int device, char uplo, int64_t n, double* A, int64_t lda, int* info);
+/* dtrsm_ (lapack.h:214-222; CMatrix::trsm CMatrix.cpp:272-295) */
+int gpc_dtrsm(int device, char side, char uplo, char transa, char diag, int64_t m, int64_t n, double alpha,
+              const double* A, int64_t lda, double* B, int64_t ldb);
+/* dsyrk_ (lapack.h:196-203; CMatrix::syrk CMatrix.cpp:297-322) */
+int gpc_dsyrk(int device, char uplo, char trans, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+              double beta, double* C, int64_t ldc);
+/* dgemm_ (lapack.h:186-194; CMatrix::gemm CMatrix.cpp:205-247) */
+int gpc_dgemm(int device, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+              int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+/* dsymv_ (lapack.h:152-160; CMatrix::symv CMatrix.cpp:127-203) */
+int gpc_dsymv(int device, char uplo, int64_t n, double alpha, const double* A, int64_t lda, const double* x,
+              double beta, double* y);
+
+/* ---- measurement helpers (bench.py) ----------------------------------------------------------------- */
+/* register-resident DMMA loop: measured fp64 tensor-pipe peak of this device in TFLOP/s */
+int gpc_bench_dmma_peak(int device, double* tflops);
+/* C(n x n) -= A(n x k) A' (lower) on device scratch: the SYRK trailing update in isolation.  *ms per launch */
+int gpc_bench_syrk(int device, int64_t n, int64_t k, int reps, double* ms);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPC_B200_H */
