@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- GP logLik+grad evaluations per second (fp64) on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] "C2": synthetic N=8192, D=8, cmpnd(rbf gamma=1/8, var=1; white
+0.01), d=1 -- SURVEY.md 8(d).  One step = one full evaluation as SCG asks of CGp (COptimisable.cpp:309-349):
+K build -> Cholesky (jitChol) -> K^-1 -> alpha -> log-likelihood terms -> hyper-parameter gradient.
+  value : evaluations/s with X and m resident in HBM (only theta changes per step)
+  e2e   : the same through the public call with HOST buffers: every step uploads X and m from pinned host memory
+          and reads ll terms + gradient back
+  roofline : the dominant kernel (DMMA GEMM/SYRK engine) -- algorithmic N^3 flop of potrf+inverse per evaluation over
+          the summed CUDA-event duration of its launches, against the measured register-resident DMMA peak
+  cpu_baseline / --impl reference : the unmodified reference (oracle/_ref) on this box's host cores, same inputs
+Multi-GPU (round 1): the path does not shard at this size -- ranks run independent replicas (one theta candidate
+each), no data-path collective; "scaling": "weak".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, D, types, natural params)
+    "c2": dict(N=8192, D=8, types=["rbf", "white"], desc="C2 synthetic N=8192 D=8 rbf(gamma=1/8,var=1)+white(0.01), d=1"),
+    "c3": dict(N=32768, D=16, types=["rbfard", "white"],
+               desc="C3 synthetic N=32768 D=16 rbfard(gamma=1/16,var=1,s_k=0.25+0.5k/15)+white(0.01), d=1"),
+}
+
+
+def make_inputs(name):
+    """X ~ N(0,1) from default_rng(20261017); y = sin(X[:,0]) + 0.1 eps, centred."""
+    w = WORKLOADS[name]
+    N, D = w["N"], w["D"]
+    rng = np.random.default_rng(20261017)
+    X = np.asfortranarray(rng.standard_normal((N, D)))
+    y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((N, 1))
+    y = np.asfortranarray(y - y.mean())
+    if name == "c2":
+        params = np.array([1.0 / D, 1.0, 0.01])
+    else:
+        params = np.concatenate([[1.0 / D, 1.0], 0.25 + 0.5 * np.arange(D) / (D - 1), [0.01]])
+    return X, y, params
+
+
+def theta_for_step(tp0, step):
+    """a slightly different theta every step, as an optimiser would ask (keeps K well conditioned)"""
+    tp = tp0.copy()
+    tp[0] += 1e-3 * ((step % 7) - 3)
+    return tp
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = []
+        for line in open(self.f.name):
+            t = [x.strip() for x in line.split(",")]
+            if len(t) >= 9 and t[0] == str(self.idx):
+                rows.append(t)
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        out["samples"] = len(rows)
+        if sm:
+            # median over the samples taken under load (>= 50% of the max seen)
+            hi = [v for v in sm if v >= 0.5 * sm[-1]]
+            out["sm_mhz"] = hi[len(hi) // 2]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        out["sm_max_mhz"] = max(mx) if mx else None
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
+        out["power_w_max"] = max(pw) if pw else None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, nm in enumerate(names):
+            if any(r[5 + i].lower().startswith("active") for r in rows):
+                out["reasons"].append(nm)
+        return out
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the UNMODIFIED reference's CPU path (oracle/_ref = GPc compiled from /root/reference,
+    OpenBLAS on all host threads) on the same workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import refbind as R
+    name = args.workload
+    w = WORKLOADS[name]
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgpcref.so missing (build with oracle/build_ref.sh)"}))
+        return
+    import gpc_b200 as G
+    X, y, params = make_inputs(name)
+    kern = G.make_kern(w["types"], w["D"])
+    kern.setParams(params)
+    tp0 = kern.getTransParams()
+    cores = os.cpu_count() or 1
+    R.set_threads(cores)
+    budget_s = float(os.environ.get("GPC_REF_BUDGET_S", "240"))
+    t_start = time.time()
+    # each step = one FULL evaluation of the workload (cold: K dirty); the number of steps is bounded by a wall
+    # budget so that the run ends within a few minutes (one C2 evaluation is ~10-20 s of host time)
+    times = []
+    warm = min(args.warmup, 1)
+    for s in range(warm + args.steps):
+        r = R.gp_eval(w["types"], theta_for_step(tp0, s), X, y)
+        if s >= warm:
+            times.append(r["t_eval"])
+        if time.time() - t_start > budget_s and times:
+            break
+    per = float(np.mean(times))
+    val = 1.0 / per
+    line = {
+        "impl": "reference", "metric": "gp_loglik_grad_evals_per_sec", "value": val, "unit": "evals/s", "n_gpus": 0,
+        "steps": len(times), "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "inputs": "identical to the gpc_b200 arm (default_rng(20261017))"},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "reference",
+                         "sample": "full %s evaluation x%d (requested %d steps; bounded by a %.0f s budget), "
+                                   "GPc -O3 + OpenBLAS %d threads" % (name.upper(), len(times), args.steps, budget_s, cores)},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpc_b200", choices=["gpc_b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra C3 (N=32768) timing")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "gpc_b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gpc_b200 as G
+    from gpc_b200._lib import check, lib, ptr
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (gpc_b200 has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    name = args.workload
+    w = WORKLOADS[name]
+    N, D = w["N"], w["D"]
+    X, y, params = make_inputs(name)
+    kern = G.make_kern(w["types"], D)
+    kern.setParams(params)
+    tp0 = kern.getTransParams()
+    P = kern.getNumParams()
+
+    ctx = G.DeviceContext(N, D, 1, device=local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    # pinned host staging of the inputs (e2e leg uploads from here every step)
+    Xp = torch.from_numpy(X.T.copy()).pin_memory()   # memory = column-major N x D
+    yp = torch.from_numpy(y.T.copy()).pin_memory()
+    ctx.set_X_ptr(Xp.data_ptr(), N, D, N)
+    ctx.set_M_ptr(yp.data_ptr(), N, 1, N)
+    out = np.zeros(3)
+    g = np.zeros(P)
+
+    def one_eval(step, upload):
+        kern.setTransParams(theta_for_step(tp0, step))
+        if upload:
+            ctx.set_X_ptr(Xp.data_ptr(), N, D, N)
+            ctx.set_M_ptr(yp.data_ptr(), N, 1, N)
+        arr, n, keep = kern._kcomps()
+        rc = check(lib().gpc_eval(ctx.handle, arr, n, 0, ptr(out), ptr(g), None))
+        if rc != 0:
+            raise SystemExit("bench: kernel matrix not positive definite (info=%d)" % rc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, upload, base):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        for s in range(nsteps):
+            one_eval(base + s, upload)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.launch_count() - l0
+
+    for s in range(args.warmup):
+        one_eval(s, True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(args.steps, False, 100)
+    phases = ctx.last_timings()
+    ms_e2e, _ = timed(args.steps, True, 200)
+    clocks = sampler.stop() if rank == 0 else {}
+    ll = -0.5 * (out[1] + out[0]) - N * 0.5 * np.log(2 * np.pi)
+
+    # ---- roofline of the dominant kernel: DMMA GEMM/SYRK launches of one evaluation, CUDA events per launch
+    check(lib().gpc_ctx_set_profile(ctx.handle, 1))
+    one_eval(300, False)
+    gms, cnt, gfl = C.c_double(0), C.c_int64(0), C.c_double(0)
+    check(lib().gpc_last_gemm_profile(ctx.handle, C.byref(gms), C.byref(cnt), C.byref(gfl)))
+    check(lib().gpc_ctx_set_profile(ctx.handle, 0))
+    peak = C.c_double(0)
+    check(lib().gpc_bench_dmma_peak(local_rank, C.byref(peak)))
+    alg_flops = float(N) ** 3  # potrf N^3/3 + inverse 2N^3/3
+    achieved = alg_flops / (gms.value * 1e-3) / 1e12 if gms.value > 0 else 0.0
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "tensor", "kernel": "dgemm_kernel (mma.sync m8n8k4 f64 = DMMA.8x8x4)", "achieved": achieved,
+        "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": traffic,
+        "peak_source": "measured on this GPU by gpc_bench_dmma_peak (register-resident DMMA loop, burst); "
+                       "MEASURED_PEAKS.json has no fp64 figure",
+        "launches_per_eval": int(cnt.value), "kernel_ms_per_eval": gms.value,
+        "algorithmic_flops_per_eval": alg_flops, "executed_flops_per_eval": gfl.value,
+        "share_of_step": gms.value / (ms_dev / args.steps) if ms_dev > 0 else None,
+    }
+
+    # ---- extra: C3 (N=32768, rbfard) single-GPU timing, the north-star "<1 s" target
+    also = None
+    if name == "c2" and not args.no_also and rank == 0:
+        try:
+            ctx.close()
+            w3 = WORKLOADS["c3"]
+            X3, y3, p3 = make_inputs("c3")
+            k3 = G.make_kern(w3["types"], w3["D"])
+            k3.setParams(p3)
+            gp3 = G.CGp(k3, X3, y3, device=local_rank)
+            ts = []
+            for rep in range(3):
+                gp3.KupToDate = False
+                t0 = time.time()
+                g3, ll3 = gp3.logLikelihoodGradient()
+                ts.append(time.time() - t0)
+            also = {"workload": w3["desc"], "seconds_per_eval": min(ts[1:]), "ll": ll3, "phases_ms": gp3.timings(),
+                    "potrf_tflops": (w3["N"] ** 3 / 3) / (gp3.timings()["potrf"] * 1e-3) / 1e12,
+                    "kbuild_gbs": 8.0 * w3["N"] ** 2 / 2 / (gp3.timings()["kbuild"] * 1e-3) / 1e9}
+            gp3.ctx.close()
+        except Exception as e:  # never lose the headline line because of the extra
+            also = {"error": str(e)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import refbind as R
+            if R.available():
+                cores = os.cpu_count() or 1
+                R.set_threads(cores)
+                r = R.gp_eval(w["types"], tp0, X, y)
+                cpu = {"value": 1.0 / r["t_eval"], "unit": "evals/s", "cores": cores, "kind": "reference",
+                       "sample": "1 full %s evaluation (GPc -O3 + OpenBLAS %d threads): cold logLikelihood %.2f s + "
+                                 "logLikelihoodGradient %.2f s" % (name.upper(), cores, r["t_ll"], r["t_grad"]),
+                       "parity": {"ll_rel": abs(ll - r["ll"]) / max(1.0, abs(r["ll"]))}}
+            else:
+                cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+        except Exception as e:
+            cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+
+    if rank == 0:
+        per_ms = ms_dev / args.steps
+        line = {
+            "metric": "gp_loglik_grad_evals_per_sec", "value": world * args.steps / (ms_dev * 1e-3), "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "parallelism": "replicas x%d (no data-path collective)" % world,
+                       "l2": "inputs larger than L2 (K, L, K^-1 = 3 x %.2f GB per evaluation)" % (8.0 * N * N / 1e9)},
+            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "evals/s",
+                    "h2d_bytes_per_step": int(8 * N * D + 8 * N), "d2h_bytes_per_step": int(8 * (8 + P) + 4)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "phases_ms": phases, "ll": ll,
+            "potrf_tflops": (N ** 3 / 3) / (phases["potrf"] * 1e-3) / 1e12,
+            "kbuild_gbs": 8.0 * N * N / 2 / (phases["kbuild"] * 1e-3) / 1e9,
+            "also": also,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,18 +25,36 @@ void set_error(const std::string& s) { g_error = s; }
 // ------------------------------------------------------------------------------------------------------
 static inline int64_t split(int64_t n) { return (n / TILE / 2) * TILE; }
 
+// every GEMM of the recursion goes through here so that profiling mode can bracket it with events
+static int gemm(const Dense& d, const GemmCall& g) {
+  if (!d.prof) return gemm(d, g);
+  GemmProf* p = d.prof;
+  if (p->used + 2 > p->ev.size()) {
+    size_t old = p->ev.size();
+    p->ev.resize(old + 1024);
+    for (size_t i = old; i < p->ev.size(); i++) GPC_CUDA_CHECK(cudaEventCreate(&p->ev[i]));
+  }
+  GPC_CUDA_CHECK(cudaEventRecord(p->ev[p->used], d.s));
+  int rc = gemm(d, g);
+  GPC_CUDA_CHECK(cudaEventRecord(p->ev[p->used + 1], d.s));
+  p->used += 2;
+  double fl = g.lower ? (double)g.m * (double)(g.m + TILE) * (double)g.k : 2.0 * (double)g.m * (double)g.n * (double)g.k;
+  p->flops.push_back(fl);
+  return rc;
+}
+
 // X L' = B, in place.  B: m x n, L: n x n lower; dbase = index of L's first row/col in the full factor
 int trsm_rlt(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n,
                     int64_t dbase) {
   if (m <= 0) return GPC_OK;
   if (n == TILE) {
     GemmCall g{B, d.Dinv + dbase * TILE, B, ldb, TILE, ldb, m, TILE, TILE, 1.0, 0.0, false, false, false};
-    return launch_gemm(g, d.s, d.launches);  // force-128 rule inside launch_gemm keeps in-place safe (n == TILE)
+    return gemm(d, g);  // force-128 rule inside launch_gemm keeps in-place safe (n == TILE)
   }
   int64_t n1 = split(n), n2 = n - n1;
   GPC_CHECK(trsm_rlt(d, B, ldb, m, L, ldl, n1, dbase));
   GemmCall g{B, L + n1, B + n1 * ldb, ldb, ldl, ldb, m, n2, n1, -1.0, 1.0, false, false, false};
-  GPC_CHECK(launch_gemm(g, d.s, d.launches));
+  GPC_CHECK(gemm(d, g));
   return trsm_rlt(d, B + n1 * ldb, ldb, m, L + n1 + n1 * ldl, ldl, n2, dbase + n1);
 }
 
@@ -46,12 +64,12 @@ int trsm_rln(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L,
   if (m <= 0) return GPC_OK;
   if (n == TILE) {
     GemmCall g{B, d.Dinv + dbase * TILE, B, ldb, TILE, ldb, m, TILE, TILE, 1.0, 0.0, false, true, false};
-    return launch_gemm(g, d.s, d.launches);
+    return gemm(d, g);
   }
   int64_t n1 = split(n), n2 = n - n1;
   GPC_CHECK(trsm_rln(d, B + n1 * ldb, ldb, m, L + n1 + n1 * ldl, ldl, n2, dbase + n1));
   GemmCall g{B + n1 * ldb, L + n1, B, ldb, ldl, ldb, m, n1, n2, -1.0, 1.0, false, true, false};
-  GPC_CHECK(launch_gemm(g, d.s, d.launches));
+  GPC_CHECK(gemm(d, g));
   return trsm_rln(d, B, ldb, m, L, ldl, n1, dbase);
 }
 
@@ -64,7 +82,7 @@ int potrf_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base) {
   GPC_CHECK(potrf_rec(d, A, lda, n1, base));
   GPC_CHECK(trsm_rlt(d, A + n1, lda, n2, A, lda, n1, base));
   GemmCall g{A + n1, A + n1, A + n1 + n1 * lda, lda, lda, lda, n2, n2, n1, -1.0, 1.0, false, false, true};
-  GPC_CHECK(launch_gemm(g, d.s, d.launches));
+  GPC_CHECK(gemm(d, g));
   return potrf_rec(d, A + n1 + n1 * lda, lda, n2, base + n1);
 }
 
@@ -75,7 +93,7 @@ int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* O
   if (n == TILE) {
     const double* Di = d.Dinv + dbase * TILE;
     GemmCall g{Di, Di, Out, TILE, TILE, ldo, TILE, TILE, TILE, 1.0, 0.0, true, true, false};
-    return launch_gemm(g, d.s, d.launches);
+    return gemm(d, g);
   }
   int64_t n1 = split(n), n2 = n - n1;
   GPC_CHECK(potri_rec(d, L, ldl, n1, Out, ldo, dbase));
@@ -85,11 +103,11 @@ int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* O
   GPC_CHECK(trsm_rln(d, X, n2, n2, L, ldl, n1, dbase));
   {  // Out21 = -Out22 * X
     GemmCall g{Out + n1 + n1 * ldo, X, Out + n1, ldo, n2, ldo, n2, n1, n2, -1.0, 0.0, false, true, false};
-    GPC_CHECK(launch_gemm(g, d.s, d.launches));
+    GPC_CHECK(gemm(d, g));
   }
   {  // Out11 -= X' * Out21 (lower), then mirror
     GemmCall g{X, Out + n1, Out, n2, ldo, ldo, n1, n1, n2, -1.0, 1.0, true, true, true};
-    GPC_CHECK(launch_gemm(g, d.s, d.launches));
+    GPC_CHECK(gemm(d, g));
     GPC_CHECK(launch_mirror_lower(Out, ldo, n1, d.s, d.launches));
   }
   return launch_transpose(Out + n1, ldo, Out + n1 * ldo, ldo, n2, n1, d.s, d.launches);
@@ -124,12 +142,16 @@ struct gpc_ctx {
   // scratch for cross-covariances (grown on demand)
   double *Xs, *Kc, *tmp1, *tmp2;
   int64_t Xs_cap, Kc_cap, tmp_cap;
+  GemmProf* prof;       // non-null in profiling mode
+  double prof_ms, prof_flops;
+  int64_t prof_count;
 };
 
 static const int SC_LOGDET = 0, SC_QUAD = 1, SC_TRACE = 2, SC_G = 8;
 
 static Dense dense_of(gpc_ctx* c) {
   Dense d;
+  d.prof = c->prof;
   d.s = c->stream;
   d.launches = &c->launches;
   d.Dinv = c->Dinv;
@@ -265,6 +287,7 @@ int gpc_ctx_destroy(gpc_ctx* c) {
   cudaFree(c->Kinv); cudaFree(c->W); cudaFree(c->Dinv); cudaFree(c->scal); cudaFree(c->info);
   cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->tmp1); cudaFree(c->tmp2);
   cudaFreeHost(c->hres); cudaFreeHost(c->hinfo);
+  gpc_ctx_set_profile(c, 0);
   for (int i = 0; i < 6; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->own_stream);
   delete c;
@@ -650,6 +673,10 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
   double jitter = 0.0;
   bool have_trace = false;
   for (int tries = 0;; tries++) {
+    if (c->prof) {
+      c->prof->used = 0;
+      c->prof->flops.clear();
+    }
     GPC_CHECK(potrf_async(c));
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[2], s));
     // optimistic: queue the rest before looking at info (a failed factorisation is rare and just redone)
@@ -687,6 +714,19 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
   if (gparams)
     for (int i = 0; i < ks.nparams; i++) gparams[i] = c->hres[SC_G + i];
   if (wantX) GPC_CHECK(download(c, gX, c->N, c->gXdev, c->Np, c->N, c->D));
+  if (c->prof) {
+    c->prof_ms = 0.0;
+    c->prof_flops = 0.0;
+    c->prof_count = (int64_t)(c->prof->used / 2);
+    for (size_t i = 0; i + 1 < c->prof->used; i += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->prof->ev[i], c->prof->ev[i + 1]);
+      c->prof_ms += ms;
+      c->prof_flops += c->prof->flops[i / 2];
+    }
+    c->prof->used = 0;
+    c->prof->flops.clear();
+  }
   for (int i = 0; i < 5; i++) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
@@ -695,6 +735,24 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
   float tot = 0.f;
   cudaEventElapsedTime(&tot, c->ev[0], c->ev[5]);
   c->last_ms[5] = tot;
+  return GPC_OK;
+}
+
+int gpc_ctx_set_profile(gpc_ctx* c, int on) {
+  if (!c) return GPC_ERR_ARG;
+  if (on && !c->prof) c->prof = new GemmProf();
+  if (!on && c->prof) {
+    for (cudaEvent_t e : c->prof->ev) cudaEventDestroy(e);
+    delete c->prof;
+    c->prof = nullptr;
+  }
+  return GPC_OK;
+}
+int gpc_last_gemm_profile(gpc_ctx* c, double* total_ms, int64_t* count, double* flops) {
+  if (!c) return GPC_ERR_ARG;
+  if (total_ms) *total_ms = c->prof_ms;
+  if (count) *count = c->prof_count;
+  if (flops) *flops = c->prof_flops;
   return GPC_OK;
 }
 

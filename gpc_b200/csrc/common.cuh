@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "../../include/gpc_b200.h"
 
 namespace gpc {
@@ -77,7 +78,13 @@ int launch_dot(const double* x, const double* y, int64_t n, double* out, cudaStr
 int launch_trtri_leaf(const double* A, int64_t lda, double* Dinv, cudaStream_t s, int64_t* launches);
 
 // ---- recursive blocked algorithms (api.cu) ---------------------------------------------------------------
+struct GemmProf {  // optional per-launch timing of the DMMA GEMM kernel (bench.py roofline)
+  std::vector<cudaEvent_t> ev;  // pairs
+  std::vector<double> flops;    // executed flops of each launch
+  size_t used = 0;
+};
 struct Dense {
+  GemmProf* prof = nullptr;
   cudaStream_t s;
   int64_t* launches;
   double* Dinv;    // n_total x TILE : inverse of diagonal block b at Dinv + b*TILE*TILE

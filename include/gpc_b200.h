@@ -143,6 +143,11 @@ int gpc_download(gpc_ctx* ctx, int which, double* dst, int64_t ld);
  * [0] K build [1] potrf [2] inverse [3] alpha+reductions [4] gradient [5] total */
 int gpc_last_timings(gpc_ctx* ctx, double* ms6);
 
+/* profiling mode (bench.py roofline): bracket every DMMA GEMM launch of gpc_eval with CUDA events on the context's
+ * stream; after an evaluation gpc_last_gemm_profile reports the summed kernel time, launch count and executed flops */
+int gpc_ctx_set_profile(gpc_ctx* ctx, int on);
+int gpc_last_gemm_profile(gpc_ctx* ctx, double* total_ms, int64_t* count, double* flops);
+
 /* ---- CMatrix level: drop-ins for the lapack.h calls CMatrix makes (host pointers, LAPACK argument meaning,
  *      scalars by value, 64-bit dimensions).  Each stages through device memory. ---------------------------*/
 /* dpotrf_ (lapack.h:59-65; CMatrix::potrf CMatrix.cpp:371-379) */
