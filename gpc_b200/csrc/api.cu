@@ -3,6 +3,8 @@
 // evaluation, and the lapack.h-level drop-ins.  Host code only orchestrates launches; there is no CPU
 // fallback: every entry point needs a CUDA device.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -11,6 +13,17 @@ namespace gpc {
 
 static thread_local std::string g_error;
 void set_error(const std::string& s) { g_error = s; }
+int trace_sync(const char* what, cudaStream_t s) {
+  static int on = -1;
+  if (on < 0) on = getenv("GPC_TRACE") ? atoi(getenv("GPC_TRACE")) : 0;
+  if (on < 2) return GPC_OK;
+  fprintf(stderr, "[gpc trace] launched %s ...", what);
+  fflush(stderr);
+  cudaError_t e = cudaStreamSynchronize(s);
+  fprintf(stderr, " %s\n", cudaGetErrorString(e));
+  fflush(stderr);
+  return e == cudaSuccess ? GPC_OK : GPC_ERR_CUDA;
+}
 
 #define GPC_CHECK(expr)             \
   do {                              \
@@ -27,7 +40,7 @@ static inline int64_t split(int64_t n) { return (n / TILE / 2) * TILE; }
 
 // every GEMM of the recursion goes through here so that profiling mode can bracket it with events
 static int gemm(const Dense& d, const GemmCall& g) {
-  if (!d.prof) return gemm(d, g);
+  if (!d.prof) return launch_gemm(g, d.s, d.launches);
   GemmProf* p = d.prof;
   if (p->used + 2 > p->ev.size()) {
     size_t old = p->ev.size();
@@ -35,7 +48,7 @@ static int gemm(const Dense& d, const GemmCall& g) {
     for (size_t i = old; i < p->ev.size(); i++) GPC_CUDA_CHECK(cudaEventCreate(&p->ev[i]));
   }
   GPC_CUDA_CHECK(cudaEventRecord(p->ev[p->used], d.s));
-  int rc = gemm(d, g);
+  int rc = launch_gemm(g, d.s, d.launches);
   GPC_CUDA_CHECK(cudaEventRecord(p->ev[p->used + 1], d.s));
   p->used += 2;
   double fl = g.lower ? (double)g.m * (double)(g.m + TILE) * (double)g.k : 2.0 * (double)g.m * (double)g.n * (double)g.k;
@@ -657,6 +670,20 @@ int gpc_posterior(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* X
   return GPC_OK;
 }
 
+static int trace_phase(gpc_ctx* c, const char* what) {
+  static int on = -1;
+  if (on < 0) on = getenv("GPC_TRACE") ? 1 : 0;
+  if (!on) return GPC_OK;
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  fprintf(stderr, "[gpc trace] %s: %s (launches so far %lld)\n", what, cudaGetErrorString(e), (long long)c->launches);
+  fflush(stderr);
+  if (e != cudaSuccess) {
+    set_error(std::string("trace: ") + what + ": " + cudaGetErrorString(e));
+    return GPC_ERR_CUDA;
+  }
+  return GPC_OK;
+}
+
 int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* out, double* gparams, double* gX) {
   GPC_CHECK(need(c, c && c->haveX && c->haveM, "gpc_eval needs X and m"));
   KSpec ks;
@@ -669,6 +696,7 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
   GPC_CHECK(launch_kbuild(ks, c->X, c->Np, c->N, c->Np, c->K, c->Np, s, &c->launches));
   c->haveK = true;
   GPC_CUDA_CHECK(cudaEventRecord(c->ev[1], s));
+  GPC_CHECK(trace_phase(c, "kbuild"));
   double jitter_used = 0.0;
   double jitter = 0.0;
   bool have_trace = false;
@@ -679,13 +707,17 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
     }
     GPC_CHECK(potrf_async(c));
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[2], s));
+    GPC_CHECK(trace_phase(c, "potrf"));
     // optimistic: queue the rest before looking at info (a failed factorisation is rare and just redone)
     GPC_CHECK(potri_rec(d, c->L, c->Np, c->Np, c->Kinv, c->Np, 0));
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[3], s));
+    GPC_CHECK(trace_phase(c, "inverse"));
     GPC_CHECK(alpha_from_inverse_async(c));
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[4], s));
+    GPC_CHECK(trace_phase(c, "alpha"));
     GPC_CHECK(grad_async(c, ks, wantX));
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[5], s));
+    GPC_CHECK(trace_phase(c, "grad"));
     GPC_CUDA_CHECK(cudaMemcpyAsync(c->hinfo, c->info, sizeof(int), cudaMemcpyDeviceToHost, s));
     GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres, c->scal, (SC_G + ks.nparams) * sizeof(double), cudaMemcpyDeviceToHost, s));
     GPC_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -236,6 +236,7 @@ int launch_kbuild(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int6
   kbuild_kernel<<<(unsigned)tiles, KTHREADS, smem, s>>>(ks, X, ldx, n, K, ldk);
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("kbuild_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
   return GPC_OK;
 }
 
@@ -278,6 +279,7 @@ int launch_kcross(const KSpec& ks, const double* X1, int64_t ldx1, int64_t n1, i
   kcross_kernel<<<grid, KTHREADS, smem, s>>>(ks, X1, ldx1, n1, X2, ldx2, n2, Kc, ldk);
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("kcross_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
   return GPC_OK;
 }
 
@@ -313,6 +315,7 @@ int launch_kdiag(const KSpec& ks, const double* X, int64_t ldx, int64_t n, doubl
   kdiag_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ks, X, ldx, n, out);
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("kdiag_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
   return GPC_OK;
 }
 
@@ -631,9 +634,11 @@ int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_
                                            gX, ldgx);
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("grad_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
   reduce_partials_kernel<<<ks.nparams, 256, 0, s>>>(partial, ctas, ks.nparams, g);
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("reduce_partials_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
   (void)np;
   return GPC_OK;
 }
@@ -663,6 +668,7 @@ int launch_row_sqnorm_sub(const double* V, int64_t ldv, int64_t rows, int64_t co
   row_sqnorm_sub_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(V, ldv, rows, cols, kdiag, var);
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("row_sqnorm_sub_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
   return GPC_OK;
 }
 // y(rows x d) = A(rows x cols) x(cols x d): thread per row
@@ -689,6 +695,7 @@ int launch_gemv_rows(const double* A, int64_t lda, int64_t rows, int64_t cols, c
   gemv_rows_kernel<<<grid, 128, 0, s>>>(A, lda, rows, cols, x, ldx, d, y, ldy);
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("gemv_rows_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
   return GPC_OK;
 }
 

@@ -83,18 +83,20 @@ def test_cholesky_inverse_matlab(matrix_mat):
 
 def test_syrk_gemm_matlab(matrix_mat):
     f = matrix_mat
-    a, b = float(f["syrkMatrixTest_alpha"]), float(f["syrkMatrixTest_beta"])
+    a, b = f["syrkMatrixTest_alpha"].item(), f["syrkMatrixTest_beta"].item()
     A, Cm, Dm = f["syrkMatrixTest_A"], f["syrkMatrixTest_C"], f["syrkMatrixTest_D"]
     for ul in "ul":   # testSyrk :332-393 (un/ln/ut/lt)
         tri = np.triu if ul == "u" else np.tril
         assert np.abs(tri(M.syrk(Cm, A, a, b, ul, "n")) - tri(f["syrkMatrixTest_SYRK1"])).max() < MATCHTOL
         assert np.abs(tri(M.syrk(Dm, A, a, b, ul, "t")) - tri(f["syrkMatrixTest_SYRK2"])).max() < MATCHTOL
-    a, b = float(f["gemmMatrixTest_alpha"]), float(f["gemmMatrixTest_beta"])
+    a, b = f["gemmMatrixTest_alpha"].item(), f["gemmMatrixTest_beta"].item()
     D_, E_, F_, G_, H_ = (f["gemmMatrixTest_" + k] for k in "DEFGH")
-    assert np.abs(M.gemm(F_, D_, E_, a, b, "n", "n") - f["gemmMatrixTest_GEMM1"]).max() < MATCHTOL   # testGemm :266-331
-    assert np.abs(M.gemm(G_, D_, H_, a, b, "t", "n") - f["gemmMatrixTest_GEMM2"]).max() < MATCHTOL
-    assert np.abs(M.gemm(F_, D_, H_, a, b, "n", "t") - f["gemmMatrixTest_GEMM3"]).max() < MATCHTOL
-    assert np.abs(M.gemm(G_, D_, E_, a, b, "t", "t") - f["gemmMatrixTest_GEMM4"]).max() < MATCHTOL
+    G1, G2 = f["gemmMatrixTest_GEMM1"], f["gemmMatrixTest_GEMM2"]
+    # testGemm :266-331: F.gemm(D,E,nn); G.gemm(D,E,tt); GEMM1.gemm(D,H,nt); GEMM2.gemm(D,H,tn)
+    assert np.abs(M.gemm(F_, D_, E_, a, b, "n", "n") - G1).max() < MATCHTOL
+    assert np.abs(M.gemm(G_, D_, E_, a, b, "t", "t") - G2).max() < MATCHTOL
+    assert np.abs(M.gemm(G1, D_, H_, a, b, "n", "t") - f["gemmMatrixTest_GEMM3"]).max() < MATCHTOL
+    assert np.abs(M.gemm(G2, D_, H_, a, b, "t", "n") - f["gemmMatrixTest_GEMM4"]).max() < MATCHTOL
 
 
 def test_trsm_all_sixteen_variants():
