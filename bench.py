@@ -309,10 +309,21 @@ def main():
                 cores = os.cpu_count() or 1
                 R.set_threads(cores)
                 r = R.gp_eval(w["types"], tp0, X, y)
+                kern.setTransParams(tp0)   # parity of this run's device result against the reference, same theta
+                ctxp = G.DeviceContext(N, D, 1, device=local_rank)
+                ctxp.set_X(X)
+                ctxp.set_M(y)
+                arr, n_, keep = kern._kcomps()
+                outp, gp_ = np.zeros(3), np.zeros(P)
+                check(lib().gpc_eval(ctxp.handle, arr, n_, 0, ptr(outp), ptr(gp_), None))
+                ctxp.close()
+                ll = -0.5 * (outp[1] + outp[0]) - N * 0.5 * np.log(2 * np.pi)
+                gtr = gp_ * kern._gradfacts()
                 cpu = {"value": 1.0 / r["t_eval"], "unit": "evals/s", "cores": cores, "kind": "reference",
                        "sample": "1 full %s evaluation (GPc -O3 + OpenBLAS %d threads): cold logLikelihood %.2f s + "
                                  "logLikelihoodGradient %.2f s" % (name.upper(), cores, r["t_ll"], r["t_grad"]),
-                       "parity": {"ll_rel": abs(ll - r["ll"]) / max(1.0, abs(r["ll"]))}}
+                       "parity": {"ll_rel": abs(ll - r["ll"]) / max(1.0, abs(r["ll"])),
+                                  "grad_rel_max": float(np.max(np.abs(gtr - r["g"]) / np.maximum(1.0, np.abs(r["g"]))))}}
             else:
                 cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
         except Exception as e:

@@ -86,34 +86,91 @@ int trsm_rln(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L,
   return trsm_rln(d, B, ldb, m, L, ldl, n1, dbase);
 }
 
-// in-place lower Cholesky of A (n x n), only the lower triangle is referenced / written
-int potrf_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base) {
-  if (n == TILE)
+// in-place lower Cholesky of A (n x n), only the lower triangle is referenced / written.
+// Look-ahead: the trailing update A22 -= A21 A21' is issued in two parts -- the top-left block that the next diagonal
+// factorisation needs on the main stream, the rest on a side stream -- and the recursion on A22 only waits for the
+// side stream (`pending`) when it first touches rows below its own first block.
+int potrf_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, cudaEvent_t pending) {
+  if (n == TILE) {
+    if (pending) GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, pending, 0));
     return launch_potrf_leaf(A, lda, d.Dinv + base * TILE, d.info, (int)base, d.nvalid - base, d.logdet, d.s,
                              d.launches);
+  }
   int64_t n1 = split(n), n2 = n - n1;
-  GPC_CHECK(potrf_rec(d, A, lda, n1, base));
+  GPC_CHECK(potrf_rec(d, A, lda, n1, base, nullptr));
+  if (pending) GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, pending, 0));
   GPC_CHECK(trsm_rlt(d, A + n1, lda, n2, A, lda, n1, base));
-  GemmCall g{A + n1, A + n1, A + n1 + n1 * lda, lda, lda, lda, n2, n2, n1, -1.0, 1.0, false, false, true};
+  double* A21 = A + n1;
+  double* A22 = A + n1 + n1 * lda;
+  if (d.fk && n2 > TILE) {
+    int64_t m1 = split(n2), m2 = n2 - m1;
+    cudaEvent_t e_trsm = d.fk->event(), e_side = d.fk->event();
+    cudaStream_t side = d.fk->stream();
+    GPC_CUDA_CHECK(cudaEventRecord(e_trsm, d.s));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(side, e_trsm, 0));
+    Dense ds = d;
+    ds.s = side;
+    {  // main: A22[0:m1,0:m1] -= A21[0:m1,:] A21[0:m1,:]'
+      GemmCall g{A21, A21, A22, lda, lda, lda, m1, m1, n1, -1.0, 1.0, false, false, true};
+      GPC_CHECK(gemm(d, g));
+    }
+    {  // side: A22[m1:,0:m1] -= A21[m1:,:] A21[0:m1,:]'   and   A22[m1:,m1:] -= A21[m1:,:] A21[m1:,:]'
+      GemmCall g1{A21 + m1, A21, A22 + m1, lda, lda, lda, m2, m1, n1, -1.0, 1.0, false, false, false};
+      GPC_CHECK(gemm(ds, g1));
+      GemmCall g2{A21 + m1, A21 + m1, A22 + m1 + m1 * lda, lda, lda, lda, m2, m2, n1, -1.0, 1.0, false, false, true};
+      GPC_CHECK(gemm(ds, g2));
+    }
+    GPC_CUDA_CHECK(cudaEventRecord(e_side, side));
+    return potrf_rec(d, A22, lda, n2, base + n1, e_side);
+  }
+  GemmCall g{A21, A21, A22, lda, lda, lda, n2, n2, n1, -1.0, 1.0, false, false, true};
   GPC_CHECK(gemm(d, g));
-  return potrf_rec(d, A + n1 + n1 * lda, lda, n2, base + n1);
+  return potrf_rec(d, A22, lda, n2, base + n1, nullptr);
+}
+
+size_t potri_workspace(int64_t n) {
+  if (n <= TILE) return 0;
+  int64_t n1 = split(n), n2 = n - n1;
+  return (size_t)n1 * n2 + potri_workspace(n1) + potri_workspace(n2);
 }
 
 // Out (n x n, full symmetric) = (L L')^-1 by the Schur-complement recursion:
 //   K^-1 = [A^-1 + X' S^-1 X, -X' S^-1; -S^-1 X, S^-1],  X = L21 L11^-1, S^-1 = (L22 L22')^-1
-int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo,
-                     int64_t dbase) {
+// The three sub-problems (A^-1, S^-1, X) are independent: with a Fork they run on separate streams.
+int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, int64_t dbase,
+              double* W) {
+  if (!W) W = d.W;
   if (n == TILE) {
     const double* Di = d.Dinv + dbase * TILE;
     GemmCall g{Di, Di, Out, TILE, TILE, ldo, TILE, TILE, TILE, 1.0, 0.0, true, true, false};
     return gemm(d, g);
   }
   int64_t n1 = split(n), n2 = n - n1;
-  GPC_CHECK(potri_rec(d, L, ldl, n1, Out, ldo, dbase));
-  GPC_CHECK(potri_rec(d, L + n1 + n1 * ldl, ldl, n2, Out + n1 + n1 * ldo, ldo, dbase + n1));
-  double* X = d.W;  // n2 x n1, ld n2
-  GPC_CHECK(launch_copy_block(L + n1, ldl, X, n2, n2, n1, 1.0, d.s, d.launches));
-  GPC_CHECK(trsm_rln(d, X, n2, n2, L, ldl, n1, dbase));
+  double* X = W;  // n2 x n1, ld n2
+  double* W1 = W + n1 * n2;
+  double* W2 = W1 + potri_workspace(n1);
+  if (d.fk && n >= 4 * TILE) {
+    cudaEvent_t e0 = d.fk->event(), e1 = d.fk->event(), e2 = d.fk->event();
+    Dense d1 = d, d2 = d;
+    d1.s = d.fk->stream();
+    d2.s = d.fk->stream();
+    GPC_CUDA_CHECK(cudaEventRecord(e0, d.s));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d1.s, e0, 0));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d2.s, e0, 0));
+    GPC_CHECK(potri_rec(d1, L, ldl, n1, Out, ldo, dbase, W1));
+    GPC_CHECK(potri_rec(d2, L + n1 + n1 * ldl, ldl, n2, Out + n1 + n1 * ldo, ldo, dbase + n1, W2));
+    GPC_CHECK(launch_copy_block(L + n1, ldl, X, n2, n2, n1, 1.0, d.s, d.launches));
+    GPC_CHECK(trsm_rln(d, X, n2, n2, L, ldl, n1, dbase));
+    GPC_CUDA_CHECK(cudaEventRecord(e1, d1.s));
+    GPC_CUDA_CHECK(cudaEventRecord(e2, d2.s));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, e1, 0));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, e2, 0));
+  } else {
+    GPC_CHECK(potri_rec(d, L, ldl, n1, Out, ldo, dbase, W1));
+    GPC_CHECK(potri_rec(d, L + n1 + n1 * ldl, ldl, n2, Out + n1 + n1 * ldo, ldo, dbase + n1, W2));
+    GPC_CHECK(launch_copy_block(L + n1, ldl, X, n2, n2, n1, 1.0, d.s, d.launches));
+    GPC_CHECK(trsm_rln(d, X, n2, n2, L, ldl, n1, dbase));
+  }
   {  // Out21 = -Out22 * X
     GemmCall g{Out + n1 + n1 * ldo, X, Out + n1, ldo, n2, ldo, n2, n1, n2, -1.0, 0.0, false, true, false};
     GPC_CHECK(gemm(d, g));
@@ -145,6 +202,7 @@ struct gpc_ctx {
   int* info;       // device
   double* partial; // grad partial sums
   double* gXdev;
+  double* symm_part;  // scratch of the alpha = K^-1 m product
   int max_ctas;
   double* hres;    // pinned host result buffer
   int* hinfo;      // pinned
@@ -155,6 +213,7 @@ struct gpc_ctx {
   // scratch for cross-covariances (grown on demand)
   double *Xs, *Kc, *tmp1, *tmp2;
   int64_t Xs_cap, Kc_cap, tmp_cap;
+  Fork* fork;           // side streams / events for the recursions
   GemmProf* prof;       // non-null in profiling mode
   double prof_ms, prof_flops;
   int64_t prof_count;
@@ -165,6 +224,7 @@ static const int SC_LOGDET = 0, SC_QUAD = 1, SC_TRACE = 2, SC_G = 8;
 static Dense dense_of(gpc_ctx* c) {
   Dense d;
   d.prof = c->prof;
+  d.fk = c->prof ? nullptr : c->fork;  // profiling mode runs serially so that per-launch durations are not overlapped
   d.s = c->stream;
   d.launches = &c->launches;
   d.Dinv = c->Dinv;
@@ -179,8 +239,8 @@ static int ensure_inverse_buffers(gpc_ctx* c) {
   if (c->Kinv) return GPC_OK;
   size_t nn = (size_t)c->Npmax * c->Npmax;
   GPC_CUDA_CHECK(cudaMalloc(&c->Kinv, nn * sizeof(double)));
-  size_t h = (size_t)(c->Npmax / 2 + TILE);
-  GPC_CUDA_CHECK(cudaMalloc(&c->W, h * h * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->W, (potri_workspace(c->Npmax) + 16) * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMalloc(&c->symm_part, (size_t)symm_chunks(c->Npmax) * 4 * c->Npmax * sizeof(double)));
   return GPC_OK;
 }
 
@@ -288,6 +348,13 @@ int gpc_ctx_create(gpc_ctx** out, int device, int64_t Nmax, int Dmax, int dout_m
   GPC_CUDA_CHECK(cudaMemset(c->M, 0, np * dout_max * sizeof(double)));
   GPC_CUDA_CHECK(cudaMemset(c->alpha, 0, np * dout_max * sizeof(double)));
   for (int i = 0; i < 6; i++) GPC_CUDA_CHECK(cudaEventCreate(&c->ev[i]));
+  if (!getenv("GPC_NO_FORK")) {
+    c->fork = new Fork();
+    c->fork->side.resize(8);
+    c->fork->ev.resize(512);
+    for (auto& st : c->fork->side) GPC_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : c->fork->ev) GPC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   *out = c;
   return GPC_OK;
 }
@@ -298,9 +365,14 @@ int gpc_ctx_destroy(gpc_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->X); cudaFree(c->M); cudaFree(c->alpha); cudaFree(c->K); cudaFree(c->L);
   cudaFree(c->Kinv); cudaFree(c->W); cudaFree(c->Dinv); cudaFree(c->scal); cudaFree(c->info);
-  cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->tmp1); cudaFree(c->tmp2);
+  cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->symm_part); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->tmp1); cudaFree(c->tmp2);
   cudaFreeHost(c->hres); cudaFreeHost(c->hinfo);
   gpc_ctx_set_profile(c, 0);
+  if (c->fork) {
+    for (auto st : c->fork->side) cudaStreamDestroy(st);
+    for (auto e : c->fork->ev) cudaEventDestroy(e);
+    delete c->fork;
+  }
   for (int i = 0; i < 6; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->own_stream);
   delete c;
@@ -498,7 +570,8 @@ int gpc_inverse(gpc_ctx* c) {
 
 static int alpha_from_inverse_async(gpc_ctx* c) {
   GPC_CUDA_CHECK(cudaMemsetAsync(c->scal + SC_QUAD, 0, sizeof(double), c->stream));
-  GPC_CHECK(launch_symm_small(c->Kinv, c->Np, c->M, c->Np, c->alpha, c->Np, c->N, c->d, nullptr, c->stream,
+  // scratch for the column-chunk partial sums: the inverse workspace W is idle once K^-1 is complete
+  GPC_CHECK(launch_symm_small(c->Kinv, c->Np, c->M, c->Np, c->alpha, c->Np, c->N, c->d, c->symm_part, c->stream,
                               &c->launches));
   return launch_dot(c->M, c->alpha, c->Np * c->d, c->scal + SC_QUAD, c->stream, &c->launches);
 }

@@ -54,6 +54,7 @@ struct GemmCall {
   bool a_kc, b_kc, lower;
 };
 int launch_gemm(const GemmCall& g, cudaStream_t s, int64_t* launches);
+void gemm_force_config(int cfg);  // -1: heuristic (default); 0..3: force a tile configuration (experiments)
 
 // potrf of one TILE x TILE diagonal block, in place (lower); also writes the inverse of the factor into
 // Dinv (TILE x TILE, ld TILE, upper part zero), adds 2*sum(log diag) to *logdet and records the first
@@ -71,9 +72,10 @@ int launch_transpose(const double* src, int64_t lds, double* dst, int64_t ldd, i
 int launch_add_diag(double* A, int64_t lda, int64_t n, double v, cudaStream_t s, int64_t* launches);
 int launch_zero_upper(double* A, int64_t lda, int64_t n, cudaStream_t s, int64_t* launches);
 int launch_set_identity_pad(double* A, int64_t lda, int64_t n, int64_t np, cudaStream_t s, int64_t* launches);
-// y(n x d) = A(n x n, full) * x(n x d) ; also *dot += sum(x .* y)
+// y(n x d) = A(n x n, full) * x(n x d); `part` is scratch of symm_chunks(n) * 4 * round_up(n, TILE) doubles
+int symm_chunks(int64_t n);
 int launch_symm_small(const double* A, int64_t lda, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
-                      int d, double* dot, cudaStream_t s, int64_t* launches);
+                      int d, double* part, cudaStream_t s, int64_t* launches);
 int launch_dot(const double* x, const double* y, int64_t n, double* out, cudaStream_t s, int64_t* launches);
 
 // inverse of the lower-triangular TILE x TILE block at A (no factorisation): Dinv as above
@@ -85,8 +87,16 @@ struct GemmProf {  // optional per-launch timing of the DMMA GEMM kernel (bench.
   std::vector<double> flops;    // executed flops of each launch
   size_t used = 0;
 };
+struct Fork {  // side streams + events for fork/join concurrency inside the recursions (owned by the context)
+  std::vector<cudaStream_t> side;
+  std::vector<cudaEvent_t> ev;
+  size_t next_s = 0, next_e = 0;
+  cudaStream_t stream() { return side[next_s++ % side.size()]; }
+  cudaEvent_t event() { return ev[next_e++ % ev.size()]; }
+};
 struct Dense {
   GemmProf* prof = nullptr;
+  Fork* fk = nullptr;  // null: everything on `s`
   cudaStream_t s;
   int64_t* launches;
   double* Dinv;    // n_total x TILE : inverse of diagonal block b at Dinv + b*TILE*TILE
@@ -97,8 +107,10 @@ struct Dense {
 };
 int trsm_rlt(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n, int64_t dbase);
 int trsm_rln(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n, int64_t dbase);
-int potrf_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base);
-int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, int64_t dbase);
+int potrf_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, cudaEvent_t pending = nullptr);
+int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, int64_t dbase,
+              double* W = nullptr);
+size_t potri_workspace(int64_t n);  // doubles needed by potri_rec for an n x n factor
 
 // ---- GP layer (gpkern.cu) -----------------------------------------------------------------------------
 // K (np x np, ld ldk): lower-triangle tiles of the kernel matrix of X (n valid rows, padded part = identity)

@@ -143,8 +143,7 @@ int gpc_dpotri(int device, char uplo, int64_t n, double* A, int64_t lda, int* in
   d.logdet = nullptr;
   d.nvalid = n;
   GPC_CHECK(sc.alloc(&d.Dinv, (size_t)np * TILE, false));
-  size_t h = (size_t)(np / 2 + TILE);
-  GPC_CHECK(sc.alloc(&d.W, h * h, false));
+  GPC_CHECK(sc.alloc(&d.W, potri_workspace(np) + 16, false));
   for (int64_t b = 0; b < np / TILE; b++)
     GPC_CHECK(launch_trtri_leaf(dl + b * TILE + b * TILE * np, np, d.Dinv + b * TILE * TILE, sc.s, &sc.launches));
   double* inv;
@@ -302,7 +301,9 @@ int gpc_dsymv(int device, char uplo, int64_t n, double alpha, const double* A, i
   GPC_CHECK(sc.alloc(&dx, (size_t)np, true));
   GPC_CHECK(sc.alloc(&dy, (size_t)np, true));
   GPC_CHECK(up(sc, dx, np, x, n, n, 1));
-  GPC_CHECK(launch_symm_small(dl, np, dx, np, dy, np, n, 1, nullptr, sc.s, &sc.launches));
+  double* part;
+  GPC_CHECK(sc.alloc(&part, (size_t)symm_chunks(n) * 4 * np, false));
+  GPC_CHECK(launch_symm_small(dl, np, dx, np, dy, np, n, 1, part, sc.s, &sc.launches));
   std::vector<double> h((size_t)n);
   GPC_CHECK(down(sc, h.data(), n, dy, np, n, 1));
   for (int64_t i = 0; i < n; i++) y[i] = alpha * h[i] + ((beta == 0.0) ? 0.0 : beta * y[i]);
@@ -357,6 +358,39 @@ int gpc_bench_dmma_peak(int device, double* tflops) {
   cudaEventDestroy(e1);
   if (tflops) *tflops = best;
   return GPC_OK;
+}
+
+int gpc_bench_gemm(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, int reps,
+                   double* ms_out) {
+  if (m % TILE || n % TILE || k % 16 || reps < 1) {
+    set_error("gpc_bench_gemm: m, n must be multiples of 128 and k of 16");
+    return GPC_ERR_ARG;
+  }
+  Scratch sc;
+  GPC_CHECK(sc.init(device));
+  double *A, *B, *C;
+  GPC_CHECK(sc.alloc(&A, (size_t)m * k, true));
+  GPC_CHECK(sc.alloc(&B, (size_t)n * k, true));
+  GPC_CHECK(sc.alloc(&C, (size_t)m * n, true));
+  GemmCall g{A, B, C, a_kc ? k : m, b_kc ? k : n, m, m, n, k, -1.0, 1.0, a_kc != 0, b_kc != 0, lower != 0};
+  gemm_force_config(cfg);
+  cudaEvent_t e0, e1;
+  GPC_CUDA_CHECK(cudaEventCreate(&e0));
+  GPC_CUDA_CHECK(cudaEventCreate(&e1));
+  int rc = launch_gemm(g, sc.s, &sc.launches);  // warm-up
+  if (rc == GPC_OK) {
+    cudaEventRecord(e0, sc.s);
+    for (int r = 0; r < reps && rc == GPC_OK; r++) rc = launch_gemm(g, sc.s, &sc.launches);
+    cudaEventRecord(e1, sc.s);
+    if (cudaStreamSynchronize(sc.s) != cudaSuccess) rc = GPC_ERR_CUDA;
+  }
+  gemm_force_config(-1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_out) *ms_out = ms / reps;
+  return rc;
 }
 
 int gpc_bench_syrk(int device, int64_t n, int64_t k, int reps, double* ms_out) {

@@ -172,6 +172,9 @@ int gpc_dsymv(int device, char uplo, int64_t n, double alpha, const double* A, i
 int gpc_bench_dmma_peak(int device, double* tflops);
 /* C(n x n) -= A(n x k) A' (lower) on device scratch: the SYRK trailing update in isolation.  *ms per launch */
 int gpc_bench_syrk(int device, int64_t n, int64_t k, int reps, double* ms);
+/* one GEMM shape on device scratch with a forced tile configuration (cfg 0..3, -1 = heuristic): kernel tuning */
+int gpc_bench_gemm(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, int reps,
+                   double* ms);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
