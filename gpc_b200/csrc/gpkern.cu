@@ -50,6 +50,45 @@ __device__ __forceinline__ void stage_rows(double* s, const double* __restrict__
   }
 }
 
+// ---- TMA staging (cp.async.bulk = SASS UBLKCP): one elected thread streams the D column segments of a 64-row X
+// tile (512 contiguous bytes each) into shared memory; completion is tracked by an mbarrier transaction count.
+// Requires the padded device layout (rows beyond n exist and are zero; every segment is 16-byte aligned).
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(src), "r"(bytes), "r"(b)
+               : "memory");
+}
+// issue the copies of rows [r0, r0+KT) x D columns into s[k*KT + r] (caller: one thread, after mbar_expect_tx)
+__device__ __forceinline__ void tma_stage_rows(double* s, const double* __restrict__ X, int64_t ldx, int64_t r0, int D,
+                                               uint64_t* bar) {
+  for (int k = 0; k < D; k++) bulk_g2s(s + k * KT, X + r0 + (int64_t)k * ldx, KT * sizeof(double), bar);
+}
+
 // pair quantities for the thread's 4x4 block
 __device__ __forceinline__ void pair_r2_dot(const double* si, const double* sj, int D, int ti, int tj, bool need_r2,
                                             bool need_dot, double (&r2)[4][4], double (&dt)[4][4]) {
@@ -194,15 +233,22 @@ __device__ __forceinline__ void tri_tile(int64_t t, int& bi, int& bj) {
 // (CKern.cpp:165-171): the generic value at r = 0 plus the white variances.  Rows/cols >= n: identity.
 __global__ void __launch_bounds__(KTHREADS) kbuild_kernel(const __grid_constant__ KSpec ks, const double* __restrict__ X,
                                                          int64_t ldx, int64_t n, double* __restrict__ K, int64_t ldk) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) uint64_t bar;
   double* si = sm;
   double* sj = sm + KT * ks.D;
   int bi, bj;
   tri_tile(blockIdx.x, bi, bj);
   const int64_t i0 = (int64_t)bi * KT, j0 = (int64_t)bj * KT;
-  stage_rows(si, X, ldx, n, i0, ks.D);
-  stage_rows(sj, X, ldx, n, j0, ks.D);
+  // X tiles through TMA bulk copies (X is stored padded: rows >= n are zero, so no bounds handling is needed)
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, 2u * KT * ks.D * (unsigned)sizeof(double));
+    tma_stage_rows(si, X, ldx, i0, ks.D, &bar);
+    tma_stage_rows(sj, X, ldx, j0, ks.D, &bar);
+  }
+  mbar_wait(&bar, 0);
   const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
   double kv[4][4];
   eval_pairs(ks, si, sj, ti, tj, kv);

@@ -95,6 +95,11 @@ class CGp:
         g, ll = self.logLikelihoodGradient()
         return -g, -ll
 
+    def optimise(self, iters=1000, verbosity=0, log=None):
+        """CGp::optimise / CGplvm::optimise -> runDefaultOptimiser -> scgOptimise (CGp.cpp:1537-1553)."""
+        from .optim import scgOptimise
+        return scgOptimise(self, maxIters=iters, verbosity=verbosity, log=log)
+
     def posteriorMeanVar(self, Xs):
         """mu, var at Xs with output scale/bias applied (CGp.cpp:561-573, 618-623)."""
         self._eval()
@@ -119,6 +124,23 @@ class CGplvm:
     """GP-LVM, plain FTC with the Gaussian latent prior (CGplvm.cpp:493-716).  Optimiser parameter order is
     [kernel trans-params][X column-major] (CGplvm.cpp:257-290).  m = (Y - bias)/scale as CScaleNoise::updateSites
     leaves it (CNoise.cpp:710-721)."""
+
+    @classmethod
+    def fromData(cls, kern, Y, latentDim=2, device=0):
+        """What `gplvm learn` builds (gplvm.cpp:504-522): CScaleNoise targets m = (Y - mean)/std (population std,
+        CNoise.cpp:576-587, 710-721) and the PCA initialisation of X (CGplvm::initXpca, CGplvm.cpp:157-222):
+        X = m U_q diag(lambda_q)^-1/2 with (lambda, U) the leading eigenpairs of cov(m), then centred."""
+        Y = np.asarray(Y, dtype=np.float64)
+        scale = np.sqrt(Y.var(axis=0))
+        scale[scale < np.finfo(np.float64).eps] = np.finfo(np.float64).eps
+        m = (Y - Y.mean(axis=0)[None, :]) / scale[None, :]
+        ymean = m.mean(axis=0)
+        cov = m.T @ m / m.shape[0] - np.outer(ymean, ymean)
+        ev, U = np.linalg.eigh(cov)
+        Winv = np.stack([U[:, -1 - i] / np.sqrt(ev[-1 - i]) for i in range(latentDim)], axis=1)
+        X0 = m @ Winv
+        X0 = X0 - X0.mean(axis=0)[None, :]
+        return cls(kern, m, X0, device)
 
     def __init__(self, kern, m, X0, device=0):
         self.pkern = kern
@@ -172,3 +194,8 @@ class CGplvm:
     def computeObjectiveGradParams(self):
         g, ll = self.logLikelihoodGradient()
         return -g, -ll
+
+    def optimise(self, iters=1000, verbosity=0, log=None):
+        """CGp::optimise / CGplvm::optimise -> runDefaultOptimiser -> scgOptimise (CGp.cpp:1537-1553)."""
+        from .optim import scgOptimise
+        return scgOptimise(self, maxIters=iters, verbosity=verbosity, log=log)

@@ -322,3 +322,19 @@ def test_full_size_properties(N, D, kind):
     gp.setOptParams(tp - h * dvec)
     lm = gp.logLikelihood()
     assert abs((lp - lm) / (2 * h) - float(g @ dvec)) < 1e-4 * max(1.0, abs(float(g @ dvec)))
+
+
+def test_gplvm_scg_trajectory_config5():
+    """BASELINE config 5 (shortened to 12 SCG iterations for test time): CGplvm.fromData on oilTrain, SCG driven by
+    the device evaluations, objective trajectory against the reference's own log (printed with 6 digits)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    Y = np.load(os.path.join(root, "tests/golden/oil_train.npz"))["Y"]
+    ref = json.load(open(os.path.join(root, "tests/golden/gplvm_c5_trajectory.json")))["objective"]
+    lvm = G.CGplvm.fromData(G.make_kern(["rbf", "bias", "white"], 2, [0.0, 0.0, -2.0, -2.0]), Y, 2)
+    log = []
+    lvm.optimise(40, log=log)
+    assert len(log) == 40
+    for a, b in zip(log, ref[:40]):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (a, b)
