@@ -126,14 +126,16 @@ class CGplvm:
     leaves it (CNoise.cpp:710-721)."""
 
     @classmethod
-    def fromData(cls, kern, Y, latentDim=2, device=0):
-        """What `gplvm learn` builds (gplvm.cpp:504-522): CScaleNoise targets m = (Y - mean)/std (population std,
-        CNoise.cpp:576-587, 710-721) and the PCA initialisation of X (CGplvm::initXpca, CGplvm.cpp:157-222):
+    def fromData(cls, kern, Y, latentDim=2, device=0, centreData=True, scaleData=False):
+        """What `gplvm learn` builds (gplvm.cpp:504-522): CScaleNoise targets m = (Y - bias)/scale with bias = column
+        means when centring (the CLI default) and scale = population std only with -S (CNoise.cpp:576-587, 710-721;
+        gplvm.cpp:506-513), and the PCA initialisation of X (CGplvm::initXpca, CGplvm.cpp:157-222):
         X = m U_q diag(lambda_q)^-1/2 with (lambda, U) the leading eigenpairs of cov(m), then centred."""
         Y = np.asarray(Y, dtype=np.float64)
-        scale = np.sqrt(Y.var(axis=0))
+        scale = np.sqrt(Y.var(axis=0)) if scaleData else np.ones(Y.shape[1])
         scale[scale < np.finfo(np.float64).eps] = np.finfo(np.float64).eps
-        m = (Y - Y.mean(axis=0)[None, :]) / scale[None, :]
+        bias = Y.mean(axis=0) if centreData else np.zeros(Y.shape[1])
+        m = (Y - bias[None, :]) / scale[None, :]
         ymean = m.mean(axis=0)
         cov = m.T @ m / m.shape[0] - np.outer(ymean, ymean)
         ev, U = np.linalg.eigh(cov)
