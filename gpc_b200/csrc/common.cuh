@@ -118,7 +118,8 @@ int launch_kbuild(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int6
                   cudaStream_t s, int64_t* launches);
 // Kc (n1p x n2p, ld ldk) = k(X1_i, X2_j) (computeElement semantics: white = 0), zero in the padding
 int launch_kcross(const KSpec& ks, const double* X1, int64_t ldx1, int64_t n1, int64_t n1p, const double* X2,
-                  int64_t ldx2, int64_t n2, int64_t n2p, double* Kc, int64_t ldk, cudaStream_t s, int64_t* launches);
+                  int64_t ldx2, int64_t n2, int64_t n2p, double* Kc, int64_t ldk, cudaStream_t s, int64_t* launches,
+                  int64_t col0 = -1);  // col0 >= 0: column block of the square training matrix (diag + identity pad)
 int launch_kdiag(const KSpec& ks, const double* X, int64_t ldx, int64_t n, double* out, cudaStream_t s,
                  int64_t* launches);
 // gradient pass.  mode 0: covGrad = -1/2 (dout*Kinv - alpha alpha')   (Kinv lower triangle read only)
@@ -127,7 +128,8 @@ int launch_kdiag(const KSpec& ks, const double* X, int64_t ldx, int64_t n, doubl
 // gX (n x D, ld ldgx) accumulated with atomics when non-null (must be zeroed by the caller).
 int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, const double* Cg, int64_t ldc,
                 const double* alpha, int64_t lda, int dout, int mode, double* partial, int max_ctas, double* g,
-                double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches);
+                double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches, int64_t col0 = -1, int64_t ncols = 0);
+                // col0 >= 0: only the lower-triangle tiles of columns [col0, col0+ncols) (multi-GPU column ownership)
 // out[i] -= / = helpers for the posterior
 int launch_row_sqnorm_sub(const double* V, int64_t ldv, int64_t rows, int64_t cols, const double* kdiag, double* var,
                           cudaStream_t s, int64_t* launches);  // var[i] = kdiag[i] - sum_j V[i,j]^2

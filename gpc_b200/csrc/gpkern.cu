@@ -287,10 +287,12 @@ int launch_kbuild(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int6
 }
 
 // ---- cross covariance K(X1, X2): full grid of 64x64 tiles, computeElement semantics, zero padding
+// col0 >= 0: the output is the column block [col0, col0 + n2p) of the square training kernel matrix of X1 (X2 = rows
+// col0.. of X1): diagonal entries get diagComputeElement semantics (+white) and the padding is the identity.
 __global__ void __launch_bounds__(KTHREADS) kcross_kernel(const __grid_constant__ KSpec ks,
                                                          const double* __restrict__ X1, int64_t ldx1, int64_t n1,
                                                          const double* __restrict__ X2, int64_t ldx2, int64_t n2,
-                                                         double* __restrict__ Kc, int64_t ldk) {
+                                                         double* __restrict__ Kc, int64_t ldk, int64_t col0) {
   extern __shared__ double sm[];
   double* si = sm;
   double* sj = sm + KT * ks.D;
@@ -301,16 +303,24 @@ __global__ void __launch_bounds__(KTHREADS) kcross_kernel(const __grid_constant_
   const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
   double kv[4][4];
   eval_pairs(ks, si, sj, ti, tj, kv);
+  const double white = (col0 >= 0) ? white_sum(ks) : 0.0;
 #pragma unroll
   for (int b = 0; b < 4; b++)
 #pragma unroll
     for (int a = 0; a < 4; a++) {
       int64_t i = i0 + ti + 16 * a, j = j0 + tj + 16 * b;
-      Kc[i + j * ldk] = (i < n1 && j < n2) ? kv[a][b] : 0.0;
+      double v = (i < n1 && j < n2) ? kv[a][b] : 0.0;
+      if (col0 >= 0) {
+        int64_t jg = col0 + j;
+        if (i == jg) v += white;
+        if (i >= n1 || j >= n2) v = (i == jg) ? 1.0 : 0.0;
+      }
+      Kc[i + j * ldk] = v;
     }
 }
 int launch_kcross(const KSpec& ks, const double* X1, int64_t ldx1, int64_t n1, int64_t n1p, const double* X2,
-                  int64_t ldx2, int64_t n2, int64_t n2p, double* Kc, int64_t ldk, cudaStream_t s, int64_t* launches) {
+                  int64_t ldx2, int64_t n2, int64_t n2p, double* Kc, int64_t ldk, cudaStream_t s, int64_t* launches,
+                  int64_t col0) {
   static bool configured = false;
   size_t smem = (size_t)2 * KT * ks.D * sizeof(double);
   if (smem > 200 * 1024) {
@@ -322,7 +332,7 @@ int launch_kcross(const KSpec& ks, const double* X1, int64_t ldx1, int64_t n1, i
     configured = true;
   }
   dim3 grid((unsigned)(n1p / KT), (unsigned)(n2p / KT));
-  kcross_kernel<<<grid, KTHREADS, smem, s>>>(ks, X1, ldx1, n1, X2, ldx2, n2, Kc, ldk);
+  kcross_kernel<<<grid, KTHREADS, smem, s>>>(ks, X1, ldx1, n1, X2, ldx2, n2, Kc, ldk, col0);
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
   if (trace_sync("kcross_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
@@ -382,8 +392,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 __global__ void __launch_bounds__(KTHREADS) grad_kernel(const __grid_constant__ KSpec ks, const double* __restrict__ X,
-                                                       int64_t ldx, int64_t n, int64_t ntiles_edge,
-                                                       const double* __restrict__ Cg, int64_t ldc,
+                                                       int64_t ldx, int64_t n, int64_t ntiles_edge, int64_t tc0,
+                                                       int64_t tc1, const double* __restrict__ Cg, int64_t ldc,
                                                        const double* __restrict__ alpha, int64_t lda, int dout,
                                                        int mode, double* __restrict__ partial, double* __restrict__ gX,
                                                        int64_t ldgx) {
@@ -400,12 +410,31 @@ __global__ void __launch_bounds__(KTHREADS) grad_kernel(const __grid_constant__ 
   const int ti = tid & 15, tj = tid >> 4;
   for (int t = tid; t < NWARP * P; t += KTHREADS) wacc[t] = 0.0;
   double* my = wacc + warp * P;
-  const int64_t total = ntiles_edge * (ntiles_edge + 1) / 2;
+  // lower-triangle tiles (bi >= bj) whose column tile bj lies in [tc0, tc1): the whole triangle for a single GPU,
+  // the owned column blocks for the multi-GPU path
+  const bool whole = (tc0 == 0 && tc1 == ntiles_edge);
+  int64_t total;
+  if (whole) {
+    total = ntiles_edge * (ntiles_edge + 1) / 2;
+  } else {
+    total = 0;
+    for (int64_t c = tc0; c < tc1; c++) total += ntiles_edge - c;
+  }
   const bool wantX = gX != nullptr;
 
   for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
     int bi, bj;
-    tri_tile(t, bi, bj);
+    if (whole) {
+      tri_tile(t, bi, bj);
+    } else {
+      int64_t rem = t, c = tc0;
+      while (rem >= ntiles_edge - c) {
+        rem -= ntiles_edge - c;
+        c++;
+      }
+      bj = (int)c;
+      bi = (int)(c + rem);
+    }
     const int64_t i0 = (int64_t)bi * KT, j0 = (int64_t)bj * KT;
     __syncthreads();
     stage_rows(si, X, ldx, n, i0, D);
@@ -661,7 +690,7 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 
 int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, const double* Cg, int64_t ldc,
                 const double* alpha, int64_t lda, int dout, int mode, double* partial, int max_ctas, double* g,
-                double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches) {
+                double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches, int64_t col0, int64_t ncols) {
   static bool configured = false;
   if (mode != 0) dout = 0;
   size_t smem = (size_t)(4 * KT * ks.D + 2 * KT * (dout > 0 ? dout : 1) + NWARP * ks.nparams) * sizeof(double);
@@ -674,10 +703,19 @@ int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_
     configured = true;
   }
   int64_t nt = (n + KT - 1) / KT;
-  int64_t total = nt * (nt + 1) / 2;
+  int64_t tc0 = 0, tc1 = nt;
+  if (col0 >= 0) {  // only the lower-triangle tiles of columns [col0, col0 + ncols)
+    tc0 = col0 / KT;
+    tc1 = (col0 + ncols + KT - 1) / KT;
+    if (tc1 > nt) tc1 = nt;
+    if (tc0 > tc1) tc0 = tc1;
+  }
+  int64_t total = 0;
+  for (int64_t c = tc0; c < tc1; c++) total += nt - c;
   int ctas = (int)(total < max_ctas ? total : max_ctas);
-  grad_kernel<<<ctas, KTHREADS, smem, s>>>(ks, X, ldx, n, nt, Cg, ldc, alpha, lda, dout > 0 ? dout : 1, mode, partial,
-                                           gX, ldgx);
+  if (ctas < 1) ctas = 1;
+  grad_kernel<<<ctas, KTHREADS, smem, s>>>(ks, X, ldx, n, nt, tc0, tc1, Cg, ldc, alpha, lda, dout > 0 ? dout : 1, mode,
+                                           partial, gX, ldgx);
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
   if (trace_sync("grad_kernel", s) != GPC_OK) return GPC_ERR_CUDA;

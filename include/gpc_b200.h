@@ -167,6 +167,33 @@ int gpc_dgemm(int device, char transa, char transb, int64_t m, int64_t n, int64_
 int gpc_dsymv(int device, char uplo, int64_t n, double alpha, const double* A, int64_t lda, const double* x,
               double beta, double* y);
 
+/* ---- device level: the same kernels on CALLER-OWNED device memory and stream.  Used by the multi-GPU path
+ *      (gpc_b200/dist.py): PyTorch owns memory, streams and the NCCL collectives; the flops run here.  All dimensions
+ *      multiples of 128 (64 for the kernel-matrix column ranges); pointers are DEVICE pointers. ------------------- */
+typedef struct gpc_dev gpc_dev;
+int gpc_dev_create(gpc_dev** out, int device, void* cuda_stream);
+int gpc_dev_destroy(gpc_dev* h);
+int gpc_dev_set_stream(gpc_dev* h, void* cuda_stream);
+int64_t gpc_dev_launch_count(gpc_dev* h);
+/* in-place lower Cholesky of one n x n diagonal block (dpotrf_ on a block of the distributed matrix); Dinv: n x 128
+ * inverses of its 128-blocks; base: global row of the block; info_dev / logdet_dev accumulate on the device */
+int gpc_dev_potrf(gpc_dev* h, double* A, int64_t lda, int64_t n, int64_t base, int64_t nvalid, double* Dinv,
+                  int* info_dev, double* logdet_dev);
+/* trans 'T': X L' = B, 'N': X L = B (dtrsm_ right/lower), B in place */
+int gpc_dev_trsm(gpc_dev* h, char trans, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n,
+                 const double* Dinv);
+/* C = alpha op(A) op(B) + beta C; a_kc / b_kc: operand stored with k contiguous; lower: only lower tiles (m == n) */
+int gpc_dev_gemm(gpc_dev* h, int a_kc, int b_kc, int lower, int64_t m, int64_t n, int64_t k, double alpha,
+                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+/* columns [col0, col0+ncols) of the training kernel matrix (CGp::_updateK semantics) into K + col0*ldk */
+int gpc_dev_kbuild_cols(gpc_dev* h, const gpc_kcomp* comps, int ncomp, const double* X, int64_t ldx, int64_t n,
+                        int64_t np, int D, int64_t col0, int64_t ncols, double* K, int64_t ldk);
+/* gradient partial sums over the lower-triangle part of columns [col0, col0+ncols) of K^-1 (Cg addresses the full
+ * matrix); natural-parameter gradients to HOST g_out (synchronises the stream) */
+int gpc_dev_grad_cols(gpc_dev* h, const gpc_kcomp* comps, int ncomp, const double* X, int64_t ldx, int64_t n, int D,
+                      int64_t col0, int64_t ncols, const double* Cg, int64_t ldc, const double* alpha, int64_t lda,
+                      int dout, double* g_out);
+
 /* ---- measurement helpers (bench.py) ----------------------------------------------------------------- */
 /* register-resident DMMA loop: measured fp64 tensor-pipe peak of this device in TFLOP/s */
 int gpc_bench_dmma_peak(int device, double* tflops);
