@@ -103,7 +103,9 @@ int gpc_dev_gemm(gpc_dev* h, int a_kc, int b_kc, int lower, int64_t m, int64_t n
                  const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
   if (!h) return GPC_ERR_ARG;
   GPC_CUDA_CHECK(cudaSetDevice(h->device));
-  GemmCall g{A, B, C, lda, ldb, ldc, m, n, k, alpha, beta, a_kc != 0, b_kc != 0, lower != 0};
+  // lower: bit 0 = lower-triangle tiles only; bit 1 = A operand zero for kk < i (k loop of row tile r0 starts at r0)
+  GemmCall g{A, B, C, lda, ldb, ldc, m, n, k, alpha, beta, a_kc != 0, b_kc != 0, (lower & 1) != 0};
+  g.ktri = (lower & 2) != 0;
   return launch_gemm(g, h->stream, &h->launches);
 }
 // columns [col0, col0+ncols) of the training kernel matrix of X (n real rows, np padded rows), all np rows,

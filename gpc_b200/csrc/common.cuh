@@ -52,6 +52,7 @@ struct GemmCall {
   int64_t m, n, k;
   double alpha, beta;
   bool a_kc, b_kc, lower;
+  bool ktri = false;  // A operand is zero for kk < i (e.g. rows of L^-T): each row tile starts its k loop at its row
 };
 int launch_gemm(const GemmCall& g, cudaStream_t s, int64_t* launches);
 void gemm_force_config(int cfg);  // -1: heuristic (default); 0..3: force a tile configuration (experiments)

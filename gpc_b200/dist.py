@@ -19,6 +19,8 @@ same code runs without a process group.
 distributed schedule under gloo (tests/test_dist_cpu.py); there is no CPU backend in this package.
 """
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -97,22 +99,25 @@ class DeviceOps:
         check(lib().gpc_dev_gemm(self._h, 0, 0, 0, Np - j0, nbj, nbk, -1.0, _ptr(Lt, j0 + k0 * Np), Np,
                                  _ptr(Lt, j0 + k0 * Np), Np, 1.0, _ptr(Lt, j0 + j0 * Np), Np))
 
-    def wt_solve(self, WTj, Lt, j0, nb, Dinv):
-        """WTj (nb x (Np-j0), ld nb) := [I 0] L_sub^-T, L_sub = L[j0:, j0:]  (rows of W' = columns of W = L^-1)"""
+    def winv_block(self, Lt, j0, nb, Dinv):
+        """Block column J of W = L^-1, returned as a contiguous tensor (nb, Np-j0): row a holds W[j0:, j0+a].
+        Computed transposed as a right-sided solve X L_sub' = [I 0] with L_sub = L[j0:, j0:]."""
         Np = Lt.shape[1]
-        WTj.zero_()
-        WTj[:nb, :].fill_diagonal_(1.0)  # tensor is (Np-j0, nb): element (r, c) of the nb x (Np-j0) matrix is [c, r]
+        WTj = self.zeros(Np - j0, nb)    # column-major nb x (Np-j0), ld nb
+        WTj[:nb, :].fill_diagonal_(1.0)
         self._sync_stream()
         check(lib().gpc_dev_trsm(self._h, b"T", _ptr(WTj), nb, nb, _ptr(Lt, j0 + j0 * Np), Np, Np - j0,
                                  _ptr(Dinv, j0 * 128)))
+        return WTj.t().contiguous()
 
-    def kinv_block(self, Kc, i0, nbi, WTi, j0, nbj, WTj, jl):
-        """Kc[i0:i0+nbi, jl:jl+nbj] = sum_{k>=i0} W[k, I] W[k, J]   (I >= J); WTi is nbi x (Np-i0), WTj nbj x (Np-j0)"""
+    def kinv_cols(self, Kc, Wc, j0, nb, jl):
+        """Kc[j0:, jl:jl+nb] = (W[:, j0:])' W[:, j0:j0+nb]  (rows i >= j0 of block column J of K^-1 = W'W): one GEMM
+        whose A operand is upper triangular (W[k, i] = 0 for k < i), so every row tile skips its zero k range."""
         Np = Kc.shape[1]
-        k = Np - i0
+        m = Np - j0
         self._sync_stream()
-        check(lib().gpc_dev_gemm(self._h, 0, 0, 0, nbi, nbj, k, 1.0, _ptr(WTi), nbi, _ptr(WTj, (i0 - j0) * nbj), nbj,
-                                 0.0, _ptr(Kc, i0 + jl * Np), Np))
+        check(lib().gpc_dev_gemm(self._h, 1, 1, 2, m, nb, m, 1.0, _ptr(Wc, j0 + j0 * Np), Np, _ptr(Wc, j0 + j0 * Np), Np,
+                                 0.0, _ptr(Kc, j0 + jl * Np), Np))
 
     def alpha_solve(self, Lt, Dinv, mt):
         """alpha = L^-T L^-1 m with the replicated factor; mt is (d, Np).  Returns alpha_t (d, Np)."""
@@ -164,7 +169,7 @@ class DistGp:
         self.Dinv = ops.zeros(Np // 128, 128, 128)
         self.owned = [b for b in range(self.nblk) if b % self.world == self.rank]
         self.Kc = ops.empty(len(self.owned) * NB, Np)  # own block columns of K^-1 (column-major Np x ncols)
-        self.WT = [None] * self.nblk
+        self.Wc = ops.zeros(Np, Np)      # W = L^-1, column-major (replicated after the all-gather; zero above the diagonal)
         self.times = {}
 
     def owner(self, b):
@@ -178,14 +183,30 @@ class DistGp:
         if self.world > 1:
             dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=self.group)
 
+    def _tick(self, name):
+        """phase timing (GPC_DIST_TIMING=1): synchronises, so only for diagnosis"""
+        if not self._timing:
+            return
+        if self.Lt.is_cuda:
+            torch.cuda.synchronize()
+        now = time.time()
+        self.times[name] = self.times.get(name, 0.0) + (now - self._t0)
+        self._t0 = now
+
     def evaluate(self):
         """returns (logdet, quad, g_natural)."""
         ops, NB, Np, nblk = self.ops, self.NB, self.Np, self.nblk
         kc = self.kern._kcomps()
         ops.reset_scalars()
+        self._timing = bool(os.environ.get("GPC_DIST_TIMING"))
+        self.times = {}
+        if self._timing and self.Lt.is_cuda:
+            torch.cuda.synchronize()
+        self._t0 = time.time()
         # ---- K build: own block columns, straight into the factor buffer
         for b in self.owned:
             ops.kbuild_cols(kc, self.Xt, self.N, self.Lt, b * NB, NB)
+        self._tick("kbuild")
         # ---- right-looking Cholesky with panel broadcasts
         for kb in range(nblk):
             k0 = kb * NB
@@ -193,6 +214,7 @@ class DistGp:
             if self.rank == src:
                 ops.potrf_block(self.Lt, k0, NB, self.N, self.Dinv.view(-1))
                 ops.trsm_panel(self.Lt, k0, NB, self.Dinv.view(-1))
+            self._tick("potrf_panel")
             if self.world > 1:
                 panel = self.Lt[k0:k0 + NB, k0:]            # nb block-column, rows k0.. (strided view)
                 buf = panel.contiguous() if self.rank == src else ops.empty(NB, Np - k0)
@@ -202,9 +224,11 @@ class DistGp:
                 if self.rank != src:
                     panel.copy_(buf)
                 del buf
+            self._tick("potrf_bcast")
             for b in self.owned:
                 if b > kb:
                     ops.update_cols(self.Lt, b * NB, NB, k0, NB)
+            self._tick("potrf_update")
         # ---- status: first non-positive pivot (max over ranks of a "first or zero" is good enough to fail loudly)
         st = torch.zeros(2, dtype=torch.float64, device=self.Lt.device)
         st[0] = ops.info[0].double()
@@ -216,22 +240,24 @@ class DistGp:
         ld_t = st[1:].clone()
         self._allreduce(ld_t)
         logdet = float(ld_t.item())
-        # ---- W = L^-1 by block columns (stored transposed), all-gathered
+        # ---- W = L^-1 by block columns, all-gathered (broadcast of the compact non-zero part of every block)
         for b in range(nblk):
             j0 = b * NB
             src = self.owner(b)
-            if self.WT[b] is None:
-                self.WT[b] = ops.empty(Np - j0, NB)
-            if self.rank == src:
-                ops.wt_solve(self.WT[b], self.Lt, j0, NB, self.Dinv.view(-1))
-            self._bcast(self.WT[b], src)
-        # ---- own block columns of K^-1 = W'W (lower part: block rows I >= J)
+            buf = ops.winv_block(self.Lt, j0, NB, self.Dinv.view(-1)) if self.rank == src else ops.empty(NB, Np - j0)
+            self._tick("winv_solve")
+            self._bcast(buf, src)
+            self.Wc[j0:j0 + NB, j0:].copy_(buf)
+            del buf
+            self._tick("winv_bcast")
+        # ---- own block columns of K^-1 = W'W (rows i >= j0)
         for jl, b in enumerate(self.owned):
-            for i in range(b, nblk):
-                ops.kinv_block(self.Kc, i * NB, NB, self.WT[i], b * NB, NB, self.WT[b], jl * NB)
+            ops.kinv_cols(self.Kc, self.Wc, b * NB, NB, jl * NB)
+        self._tick("kinv_gemm")
         # ---- alpha (replicated), quadratic form
         alpha_t = ops.alpha_solve(self.Lt, self.Dinv.view(-1), self.mt)
         quad = float((alpha_t * self.mt).sum().item())
+        self._tick("alpha")
         # ---- gradient partial sums over the owned columns
         g = None
         for jl, b in enumerate(self.owned):
@@ -241,6 +267,7 @@ class DistGp:
             g = np.zeros(self.kern.getNumParams())
         gt = torch.from_numpy(g).to(self.Lt.device)
         self._allreduce(gt)
+        self._tick("grad")
         return logdet, quad, gt.cpu().numpy()
 
     def logLikelihoodGradient(self):

@@ -182,7 +182,8 @@ int gpc_dev_potrf(gpc_dev* h, double* A, int64_t lda, int64_t n, int64_t base, i
 /* trans 'T': X L' = B, 'N': X L = B (dtrsm_ right/lower), B in place */
 int gpc_dev_trsm(gpc_dev* h, char trans, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n,
                  const double* Dinv);
-/* C = alpha op(A) op(B) + beta C; a_kc / b_kc: operand stored with k contiguous; lower: only lower tiles (m == n) */
+/* C = alpha op(A) op(B) + beta C; a_kc / b_kc: operand stored with k contiguous; lower bit 0: only lower tiles
+ * (m == n); lower bit 1: op(A)(i, kk) is zero for kk < i, so the k loop of each row tile starts at its first row */
 int gpc_dev_gemm(gpc_dev* h, int a_kc, int b_kc, int lower, int64_t m, int64_t n, int64_t k, double alpha,
                  const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
 /* columns [col0, col0+ncols) of the training kernel matrix (CGp::_updateK semantics) into K + col0*ldk */

@@ -75,17 +75,19 @@ class FakeOps:
         C_ = Lt[j0:j0 + nbj, j0:].numpy().T
         Lt[j0:j0 + nbj, j0:] = torch.from_numpy((C_ - A @ Bm.T).T.copy())
 
-    def wt_solve(self, WTj, Lt, j0, nb, Dinv):
+    def winv_block(self, Lt, j0, nb, Dinv):
         Lsub = np.tril(Lt[j0:, j0:].numpy().T)
         E = np.zeros((Lsub.shape[0], nb))
         E[:nb] = np.eye(nb)
-        W = np.linalg.solve(Lsub, E)                      # (Np-j0) x nb
-        WTj.copy_(torch.from_numpy(W.copy()))             # tensor (Np-j0, nb) == column-major nb x (Np-j0) of W'
+        import scipy.linalg as sla
+        W = sla.solve_triangular(Lsub, E, lower=True)     # (Np-j0) x nb = W[j0:, J]; exact zeros above the diagonal
+        return torch.from_numpy(W.T.copy())               # (nb, Np-j0): row a = W[j0:, j0+a]
 
-    def kinv_block(self, Kc, i0, nbi, WTi, j0, nbj, WTj, jl):
-        Wi = WTi.numpy()                                  # (Np-i0) x nbi
-        Wj = WTj.numpy()[i0 - j0:]                        # rows k >= i0
-        Kc[jl:jl + nbj, i0:i0 + nbi] = torch.from_numpy((Wi.T @ Wj).T.copy())
+    def kinv_cols(self, Kc, Wc, j0, nb, jl):
+        W = Wc.numpy().T                                  # W[k, i]
+        assert np.all(np.triu(W, 1) == 0.0)               # the schedule must leave W lower triangular
+        blk = W[j0:, j0:].T @ W[j0:, j0:j0 + nb]          # (Np-j0) x nb
+        Kc[jl:jl + nb, j0:] = torch.from_numpy(blk.T.copy())
 
     def alpha_solve(self, Lt, Dinv, mt):
         L = np.tril(Lt.numpy().T)

@@ -53,6 +53,6 @@ for rep in range(reps):
 if rank == 0:
     print(json.dumps({"workload": wl, "N": N, "D": D, "NB": NB, "world": world, "seconds": ts, "best": min(ts), "ll": ll,
                       "g": list(map(float, g[:4])), "tflops_equiv": N ** 3 / min(ts) / 1e12,
-                      "mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+                      "mem_gb": torch.cuda.max_memory_allocated() / 1e9, "phases_s": gp.times}))
 if world > 1:
     dist.destroy_process_group()
