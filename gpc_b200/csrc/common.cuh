@@ -55,7 +55,15 @@ struct GemmCall {
   bool ktri = false;  // A operand is zero for kk < i (e.g. rows of L^-T): each row tile starts its k loop at its row
 };
 int launch_gemm(const GemmCall& g, cudaStream_t s, int64_t* launches);
-void gemm_force_config(int cfg);  // -1: heuristic (default); 0..3: force a tile configuration (experiments)
+void gemm_force_config(int cfg);  // -1: heuristic (default); 0..4: force a DMMA tile configuration; 100+S: Ozaki, S slices
+
+// ---- fp64 GEMM on the INT8 tensor pipe (ozaki.cu: tcgen05.mma.kind::i8 + TMEM + TMA, error-free splitting) --------
+// on < 0 / slices == 0 / min_* <= 0 leave the respective setting unchanged.  Defaults come from the environment:
+// GPC_OZAKI (0/1), GPC_OZAKI_SLICES (2..8), GPC_OZAKI_MIN_MN, GPC_OZAKI_MIN_K.
+void oz_configure(int on, int slices, int64_t min_mn, int64_t min_k);
+bool oz_wants(const GemmCall& g);  // true when launch_gemm should route this call to launch_gemm_ozaki
+int launch_gemm_ozaki(const GemmCall& g, cudaStream_t s, int64_t* launches, int slices = 0);  // 0: configured
+void oz_release_device(int dev);   // frees the per-device slice workspace
 
 // potrf of one TILE x TILE diagonal block, in place (lower); also writes the inverse of the factor into
 // Dinv (TILE x TILE, ld TILE, upper part zero), adds 2*sum(log diag) to *logdet and records the first

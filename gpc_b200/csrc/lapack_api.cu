@@ -393,6 +393,40 @@ int gpc_bench_gemm(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_
   return rc;
 }
 
+int gpc_set_gemm_engine(int ozaki, int slices, int64_t min_mn, int64_t min_k) {
+  if (slices != 0 && (slices < 2 || slices > 8)) {
+    set_error("gpc_set_gemm_engine: slices must be 2..8");
+    return GPC_ERR_ARG;
+  }
+  oz_configure(ozaki, slices, min_mn, min_k);
+  return GPC_OK;
+}
+
+int gpc_gemm_check(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, double alpha,
+                   double beta, const double* A, const double* B, double* C) {
+  if (m % TILE || n % TILE || k % 128 || m < TILE || n < TILE || k < 128 || !A || !B || !C) {
+    set_error("gpc_gemm_check: m, n, k must be positive multiples of 128");
+    return GPC_ERR_ARG;
+  }
+  Scratch sc;
+  GPC_CHECK(sc.init(device));
+  double *dA, *dB, *dC;
+  GPC_CHECK(sc.alloc(&dA, (size_t)m * k, false));
+  GPC_CHECK(sc.alloc(&dB, (size_t)n * k, false));
+  GPC_CHECK(sc.alloc(&dC, (size_t)m * n, false));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(dA, A, (size_t)m * k * sizeof(double), cudaMemcpyHostToDevice, sc.s));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(dB, B, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice, sc.s));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(dC, C, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice, sc.s));
+  GemmCall g{dA, dB, dC, a_kc ? k : m, b_kc ? k : n, m, m, n, k, alpha, beta, a_kc != 0, b_kc != 0, lower != 0};
+  gemm_force_config(cfg);
+  int rc = launch_gemm(g, sc.s, &sc.launches);
+  gemm_force_config(-1);
+  if (rc != GPC_OK) return rc;
+  GPC_CUDA_CHECK(cudaMemcpyAsync(C, dC, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost, sc.s));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(sc.s));
+  return GPC_OK;
+}
+
 int gpc_bench_syrk(int device, int64_t n, int64_t k, int reps, double* ms_out) {
   if (n % TILE || k % 16 || n < TILE || k < 16 || reps < 1) {
     set_error("gpc_bench_syrk: n must be a multiple of 128 and k of 16");

@@ -1,0 +1,650 @@
+// ozaki.cu -- fp64 GEMM/SYRK on the 5th-generation tensor cores of sm_100a (tcgen05 + TMEM + TMA).
+//
+// tcgen05.mma has no f64 kind, and the legacy DMMA path (dense.cu) tops out at 37 TFLOP/s.  The large trailing
+// updates of the blocked Cholesky / inverse (the dsyrk_/dgemm_ work below dpotrf_/dpotri_, reference
+// lapack.h:59-73, CMatrix.cpp:371-432) are therefore computed with the error-free "Ozaki" splitting on the INT8
+// tensor pipe (tcgen05.mma.kind::i8, exact int32 accumulation in TMEM):
+//
+//   a_ik = 2^ea_i * sum_p A_p[i,k] 2^-(7p-1),  A_p int8 in [-64, 64]   (row-wise exponent, balanced base-128 digits)
+//   C_ij = 2^(ea_i+eb_j) * sum_{c=2}^{S+1} 2^-(7c-2) * ( sum_{p+q=c} A_p B_q' )_ij
+//
+// Every int8 product is exact; products of equal weight c = p+q share one int32 TMEM accumulator ("level"), so one
+// 128 x 64 output tile owns S levels x 64 columns = all 512 TMEM columns for S = 8.  The S levels are combined in
+// fp64 (Horner, exact power-of-two scalings) by the epilogue warps.  With S = 8 the operands are represented to
+// 55 bits below the row maximum (fp64 has 53), S(S+1)/2 = 36 int8 MMAs replace one fp64 MMA.
+//
+// Kernel anatomy (one CTA per output tile, 6 warps):
+//   warp 4 lane 0 : TMA producer -- slices are K-major int8 [slice][row][k]; a k-block (128 B of k) of all S B-slices
+//                   (64 rows each, stacked along N) goes to one of two B sets, the A-slices (128 rows) stream through
+//                   a ring of 16 KB slots.  128-byte swizzle, mbarrier transaction counts.
+//   warp 5 lane 0 : MMA issuer -- for A_p the B slices q = 1..S+1-p are contiguous in smem, so ONE instruction with
+//                   N = 64*(S+1-p) (<= 256) feeds S+1-p consecutive levels; tcgen05.commit releases smem slots.
+//   warps 0-3     : epilogue -- tcgen05.ld 32x32b (one TMEM lane = one output row per thread), Horner over the levels,
+//                   scale by 2^(ea_i+eb_j), C = alpha*acc + beta*C, coalesced column-major stores.
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <mutex>
+#include "common.cuh"
+
+#define GPC_CHECK(expr)            \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != GPC_OK) return _rc; \
+  } while (0)
+
+namespace gpc {
+
+constexpr int OZ_BM = 128;        // output tile rows (= TMEM lanes, UMMA M)
+constexpr int OZ_BN = 64;         // output tile columns per level
+constexpr int OZ_BK = 128;        // bytes (= int8 elements) of k per k-block: one 128B-swizzle row
+constexpr int OZ_UK = 32;         // k per tcgen05.mma.kind::i8
+constexpr int OZ_MAXS = 8;        // slices (levels); S*OZ_BN <= 512 TMEM columns
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_A_BYTES = OZ_BM * OZ_BK;   // 16 KB per A-slice slot
+constexpr int OZ_B_BYTES = OZ_BN * OZ_BK;   //  8 KB per B-slice tile
+constexpr int OZ_MAXNA = 8;
+constexpr long long OZ_SPIN_LIMIT = 4000000000LL;  // ~2 s of clock64: a protocol error traps instead of hanging the GPU
+
+// ------------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void oz_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void oz_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t oz_mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity, int* errflag, int code) {
+  if (oz_mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!oz_mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > OZ_SPIN_LIMIT) {
+      if (errflag) atomicExch(errflag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void oz_tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void oz_prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void oz_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void oz_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void oz_tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]', int8 x int8 -> int32
+__device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// instruction descriptor: D = S32 (2 @bit4), A = B = signed int8 (1 @bit7, 1 @bit10), both K-major, N>>3 @bit17, M>>4 @bit24
+__device__ __forceinline__ uint32_t oz_idesc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+}
+__device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, int (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Slicing: fp64 operand (R rows = the m or n index, K deep) -> S int8 slices, K-major [slice][row][k], + row scales
+//   kc = 1: element (r, kk) at g[kk + r*ld];   kc = 0: element (r, kk) at g[r + kk*ld]
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict__ g, int64_t ld, int kc, int64_t K,
+                                                       int64_t kchunk, int* __restrict__ emax) {
+  const int tid = threadIdx.x;
+  const int64_t k0 = (int64_t)blockIdx.y * kchunk;
+  const int64_t k1 = (k0 + kchunk < K) ? k0 + kchunk : K;
+  if (!kc) {
+    // 128 rows per block; thread pair (h = 0/1) strides over kk
+    const int64_t r = (int64_t)blockIdx.x * 128 + (tid & 127);
+    int e = 0;
+    for (int64_t kk = k0 + (tid >> 7); kk < k1; kk += 2) {
+      unsigned hi = (unsigned)__double2hiint(g[r + kk * ld]);
+      int ex = (int)((hi >> 20) & 0x7ffu);
+      e = ex > e ? ex : e;
+    }
+    atomicMax(&emax[r], e);
+  } else {
+    // 128 rows per block, 16 per warp, lanes sweep along k
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int i = 0; i < 16; i++) {
+      const int64_t r = (int64_t)blockIdx.x * 128 + warp * 16 + i;
+      int e = 0;
+      for (int64_t kk = k0 + lane; kk < k1; kk += 32) {
+        unsigned hi = (unsigned)__double2hiint(g[kk + r * ld]);
+        int ex = (int)((hi >> 20) & 0x7ffu);
+        e = ex > e ? ex : e;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        int t = __shfl_xor_sync(0xffffffffu, e, o);
+        e = t > e ? t : e;
+      }
+      if (lane == 0) atomicMax(&emax[r], e);
+    }
+  }
+}
+
+constexpr int OZ_SL_ROWS = 32;            // rows per slicing block
+constexpr int OZ_SL_STRIDE = OZ_BK + 4;   // 132-byte smem row stride: conflict-free byte scatter for both layouts
+
+template <int S>
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ g, int64_t ld, int kc, int64_t Rpad,
+                                                      int64_t Kpad, const int* __restrict__ emax,
+                                                      int8_t* __restrict__ out, double* __restrict__ scale) {
+  __shared__ __align__(16) int8_t sm[S * OZ_SL_ROWS * OZ_SL_STRIDE];
+  __shared__ double s_inv[OZ_SL_ROWS];
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * OZ_SL_ROWS;
+  const int64_t k0 = (int64_t)blockIdx.y * OZ_BK;
+  if (tid < OZ_SL_ROWS) {
+    // |x| < 2^(E-1022) for every x of the row (E = largest biased exponent); x' = x * 2^-(E-1022) in (-1, 1)
+    int E = emax[r0 + tid];
+    double inv, sc;
+    if (E >= 2047) {  // Inf / NaN in the row: poison the row's outputs instead of silently slicing garbage
+      inv = 0.0;
+      sc = __longlong_as_double(0x7ff8000000000000LL);
+    } else {
+      int Ec = E < 2 ? 2 : (E > 2044 ? 2044 : E);
+      inv = __longlong_as_double((long long)(2045 - Ec) << 52);  // 2^-(Ec-1022)
+      sc = __longlong_as_double((long long)(Ec + 1) << 52);      // 2^(Ec-1022)
+    }
+    s_inv[tid] = inv;
+    if (blockIdx.y == 0) scale[r0 + tid] = sc;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int i = 0; i < (OZ_SL_ROWS * OZ_BK) / 256; i++) {
+    int r, kk;
+    double x;
+    if (!kc) {
+      r = tid & 31;
+      kk = (tid >> 5) + 8 * i;
+      x = g[(r0 + r) + (k0 + kk) * ld];
+    } else {
+      kk = tid & 127;
+      r = (tid >> 7) + 2 * i;
+      x = g[(k0 + kk) + (r0 + r) * ld];
+    }
+    double v = x * s_inv[r] * 64.0;
+    int8_t* dst = sm + r * OZ_SL_STRIDE + kk;
+#pragma unroll
+    for (int p = 0; p < S; p++) {
+      double dg = rint(v);
+      dst[p * (OZ_SL_ROWS * OZ_SL_STRIDE)] = (int8_t)(int)dg;
+      v = (v - dg) * 128.0;
+    }
+  }
+  __syncthreads();
+  // write out: S * 32 rows of 128 contiguous bytes, 16 B per thread
+  for (int c = tid; c < S * OZ_SL_ROWS * (OZ_BK / 16); c += 256) {
+    const int p = c / (OZ_SL_ROWS * 8), rem = c % (OZ_SL_ROWS * 8);
+    const int r = rem >> 3, ch = rem & 7;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(sm + p * (OZ_SL_ROWS * OZ_SL_STRIDE) + r * OZ_SL_STRIDE + ch * 16);
+    uint4 v4 = make_uint4(src[0], src[1], src[2], src[3]);
+    *reinterpret_cast<uint4*>(out + ((int64_t)p * Rpad + r0 + r) * Kpad + k0 + ch * 16) = v4;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// The tcgen05 GEMM
+// ------------------------------------------------------------------------------------------------------
+struct OzArgs {
+  double* C;
+  int64_t ldc;
+  const double* scaleA;  // 2^ea_i per row of A
+  const double* scaleB;  // 2^eb_j per row of B (= column of C)
+  double alpha, beta;
+  int tiles_m, tiles_n;
+  int kblocks;           // K / 128
+  int S, NA;
+  int lower;             // skip tiles strictly above the diagonal
+  int ktri;              // A rows are zero for kk < row: start the k loop at the tile's first row
+  int RpadA, RpadB;      // padded row counts (slice stride in the tensor maps)
+  int* errflag;
+};
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzArgs a) {
+  extern __shared__ uint8_t oz_smem_raw[];
+  // ---- which tile (grouped raster: 8 row tiles share the B panels that stream through L2)
+  int bm, bn;
+  {
+    const int GM = 8;
+    const int t = blockIdx.x;
+    const int per_group = GM * a.tiles_n;
+    const int grp = t / per_group, rem = t % per_group;
+    const int first = grp * GM;
+    const int gsz = (a.tiles_m - first) < GM ? (a.tiles_m - first) : GM;
+    bm = first + rem % gsz;
+    bn = rem / gsz;
+  }
+  if (a.lower && bn > 2 * bm + 1) return;  // whole CTA, before any barrier / TMEM allocation
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = a.S, NA = a.NA;
+  const int m0 = bm * OZ_BM, n0 = bn * OZ_BN;
+  const int kb0 = a.ktri ? (m0 / OZ_BK) : 0;
+  const int KB = a.kblocks;
+
+  // ---- shared memory carve-up (1024-byte aligned for the 128B swizzle atoms)
+  const uint32_t raw = smem_u32(oz_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = oz_smem_raw + (base - raw);
+  const uint32_t sB = base;                                   // 2 sets x S x 8 KB
+  const uint32_t sA = sB + 2u * S * OZ_B_BYTES;               // NA x 16 KB
+  uint8_t* tail = gbase + 2u * S * OZ_B_BYTES + (uint32_t)NA * OZ_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);         // full_a[8] empty_a[8] full_b[2] empty_b[2] tmem_full
+  double* s_cscale = reinterpret_cast<double*>(tail + 256);   // 64 doubles
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tail + 256 + 512);
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL_A = [&](int i) { return bar0 + 8u * i; };
+  auto EMPTY_A = [&](int i) { return bar0 + 8u * (OZ_MAXNA + i); };
+  auto FULL_B = [&](int i) { return bar0 + 8u * (2 * OZ_MAXNA + i); };
+  auto EMPTY_B = [&](int i) { return bar0 + 8u * (2 * OZ_MAXNA + 2 + i); };
+  const uint32_t TMEM_FULL = bar0 + 8u * (2 * OZ_MAXNA + 4);
+
+  if (warp == 4 && lane == 0) {
+    for (int i = 0; i < OZ_MAXNA; i++) {
+      oz_mbar_init(FULL_A(i), 1);
+      oz_mbar_init(EMPTY_A(i), 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      oz_mbar_init(FULL_B(i), 1);
+      oz_mbar_init(EMPTY_B(i), 1);
+    }
+    oz_mbar_init(TMEM_FULL, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    oz_prefetch_tmap(&tmA);
+    oz_prefetch_tmap(&tmB);
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  oz_tc_fence_before();
+  __syncthreads();
+  oz_tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t ia = 0;
+      for (int kb = kb0; kb < KB; kb++) {
+        const int it = kb - kb0, set = it & 1;
+        if (it >= 2) oz_mbar_wait(EMPTY_B(set), ((it >> 1) - 1) & 1, a.errflag, 1);
+        oz_mbar_expect_tx(FULL_B(set), (uint32_t)S * OZ_B_BYTES);
+        for (int q = 0; q < S; q++)
+          oz_tma_load_2d(sB + (uint32_t)(set * S + q) * OZ_B_BYTES, &tmB, FULL_B(set), kb * OZ_BK, q * a.RpadB + n0);
+        for (int p = 0; p < S; p++, ia++) {
+          const uint32_t slot = ia % NA, round = ia / NA;
+          if (round >= 1) oz_mbar_wait(EMPTY_A(slot), (round - 1) & 1, a.errflag, 2);
+          oz_mbar_expect_tx(FULL_A(slot), OZ_A_BYTES);
+          oz_tma_load_2d(sA + slot * OZ_A_BYTES, &tmA, FULL_A(slot), kb * OZ_BK, p * a.RpadA + m0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      uint32_t ia = 0;
+      for (int kb = kb0; kb < KB; kb++) {
+        const int it = kb - kb0, set = it & 1;
+        oz_mbar_wait(FULL_B(set), (it >> 1) & 1, a.errflag, 3);
+        oz_tc_fence_after();
+        const uint32_t b_base = sB + (uint32_t)(set * S) * OZ_B_BYTES;
+        for (int p = 0; p < S; p++, ia++) {
+          const uint32_t slot = ia % NA, round = ia / NA;
+          oz_mbar_wait(FULL_A(slot), round & 1, a.errflag, 4);
+          oz_tc_fence_after();
+          const uint32_t a_base = sA + slot * OZ_A_BYTES;
+          const int cnt = S - p;  // B slices q = 0..cnt-1 pair with A slice p; level = p + q
+#pragma unroll
+          for (int ks = 0; ks < OZ_BK / OZ_UK; ks++) {
+            const uint64_t adesc = oz_smem_desc(a_base + ks * OZ_UK);
+            for (int q0 = 0; q0 < cnt; q0 += 4) {
+              const int nq = (cnt - q0) < 4 ? (cnt - q0) : 4;
+              const uint64_t bdesc = oz_smem_desc(b_base + (uint32_t)q0 * OZ_B_BYTES + ks * OZ_UK);
+              const uint32_t acc = (it == 0 && ks == 0 && p == 0) ? 0u : 1u;  // A slice 0 touches every level first
+              oz_mma_i8(tmem + (uint32_t)(p + q0) * OZ_BN, adesc, bdesc, oz_idesc(nq * OZ_BN), acc);
+            }
+          }
+          oz_tc_commit(EMPTY_A(slot));
+        }
+        oz_tc_commit(EMPTY_B(set));
+      }
+      oz_tc_commit(TMEM_FULL);
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps 0..3: TMEM lane = output row =====
+    if (tid < OZ_BN) s_cscale[tid] = a.scaleB[n0 + tid];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int row = warp * 32 + lane;
+    const double rs = a.scaleA[m0 + row] * (1.0 / 4096.0);  // 2^-12: weight of level c = 2
+    const double alpha = a.alpha, beta = a.beta;
+    oz_mbar_wait(TMEM_FULL, 0, a.errflag, 5);
+    oz_tc_fence_after();
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    double* crow = a.C + (int64_t)(m0 + row) + (int64_t)n0 * a.ldc;
+#pragma unroll 1
+    for (int ch = 0; ch < OZ_BN / 16; ch++) {
+      double acc[16];
+      int r[16];
+      oz_tmem_ld16(trow + (uint32_t)((S - 1) * OZ_BN + ch * 16), r);
+#pragma unroll
+      for (int j = 0; j < 16; j++) acc[j] = (double)r[j];
+      for (int l = S - 2; l >= 0; l--) {
+        oz_tmem_ld16(trow + (uint32_t)(l * OZ_BN + ch * 16), r);
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] = fma(acc[j], 0.0078125, (double)r[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        double v = alpha * (acc[j] * rs * s_cscale[ch * 16 + j]);
+        double* p = crow + (int64_t)(ch * 16 + j) * a.ldc;
+        if (beta != 0.0) v = fma(beta, *p, v);
+        *p = v;
+      }
+    }
+  }
+  oz_tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    oz_tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmap_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmap_encode get_encode() {
+  static PFN_tmap_encode fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmap_encode)p;
+  }
+  return fn;
+}
+
+// int8 slices [S*Rpad rows][Kpad] K-major; box = 128 bytes of k x box_rows rows, 128B swizzle
+static int make_tmap(CUtensorMap* tm, const int8_t* base, int64_t rows_total, int64_t Kpad, int box_rows) {
+  PFN_tmap_encode enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return GPC_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows_total};
+  cuuint64_t gstr[1] = {(cuuint64_t)Kpad};
+  cuuint32_t box[2] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return GPC_ERR_CUDA;
+  }
+  return GPC_OK;
+}
+
+// One workspace per device, shared by all streams: Ozaki GEMMs fill the whole GPU, so they are serialised
+// through `done` instead of giving every side stream its own multi-GB slice buffers.
+struct OzWorkspace {
+  int8_t* sl[2] = {nullptr, nullptr};
+  size_t cap[2] = {0, 0};
+  int* emax[2] = {nullptr, nullptr};
+  double* scale[2] = {nullptr, nullptr};
+  size_t rcap[2] = {0, 0};
+  int* errflag = nullptr;
+  cudaEvent_t done = nullptr;
+  bool used = false;
+};
+static std::mutex g_oz_mu;
+static OzWorkspace g_oz_ws[64];
+
+static int g_oz_on = -1, g_oz_S = 8;
+static int64_t g_oz_min_mn = 1024, g_oz_min_k = 1024;
+static void oz_init_settings() {
+  if (g_oz_on >= 0) return;
+  const char* e = getenv("GPC_OZAKI");
+  g_oz_on = e ? atoi(e) : 0;
+  if ((e = getenv("GPC_OZAKI_SLICES"))) g_oz_S = atoi(e);
+  if ((e = getenv("GPC_OZAKI_MIN_MN"))) g_oz_min_mn = atoll(e);
+  if ((e = getenv("GPC_OZAKI_MIN_K"))) g_oz_min_k = atoll(e);
+  if (g_oz_S < 2) g_oz_S = 2;
+  if (g_oz_S > OZ_MAXS) g_oz_S = OZ_MAXS;
+}
+void oz_configure(int on, int slices, int64_t min_mn, int64_t min_k) {
+  oz_init_settings();
+  if (on >= 0) g_oz_on = on;
+  if (slices >= 2 && slices <= OZ_MAXS) g_oz_S = slices;
+  if (min_mn > 0) g_oz_min_mn = min_mn;
+  if (min_k > 0) g_oz_min_k = min_k;
+}
+bool oz_wants(const GemmCall& c) {
+  oz_init_settings();
+  if (!g_oz_on) return false;
+  if (c.C == c.A || c.C == c.B) return false;
+  if (c.m % OZ_BM || c.n % OZ_BN || c.k % OZ_BK) return false;
+  if (c.m < g_oz_min_mn || c.n < g_oz_min_mn || c.k < g_oz_min_k) return false;
+  if (c.k > 32768) return false;  // int32 level accumulators: (S) * k * 64^2 < 2^31
+  if (c.m * (int64_t)OZ_MAXS >= (1LL << 31) || c.n * (int64_t)OZ_MAXS >= (1LL << 31)) return false;
+  return true;
+}
+
+static int ensure_ws(OzWorkspace& w, int which, size_t bytes, size_t rows) {
+  if (!w.done) {
+    GPC_CUDA_CHECK(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    GPC_CUDA_CHECK(cudaMalloc(&w.errflag, sizeof(int)));
+    GPC_CUDA_CHECK(cudaMemset(w.errflag, 0, sizeof(int)));
+  }
+  if (w.cap[which] < bytes) {
+    if (w.sl[which]) GPC_CUDA_CHECK(cudaFree(w.sl[which]));  // implicit device synchronisation
+    w.sl[which] = nullptr;
+    w.cap[which] = 0;
+    GPC_CUDA_CHECK(cudaMalloc(&w.sl[which], bytes));
+    w.cap[which] = bytes;
+  }
+  if (w.rcap[which] < rows) {
+    if (w.emax[which]) GPC_CUDA_CHECK(cudaFree(w.emax[which]));
+    if (w.scale[which]) GPC_CUDA_CHECK(cudaFree(w.scale[which]));
+    w.emax[which] = nullptr;
+    w.scale[which] = nullptr;
+    w.rcap[which] = 0;
+    GPC_CUDA_CHECK(cudaMalloc(&w.emax[which], rows * sizeof(int)));
+    GPC_CUDA_CHECK(cudaMalloc(&w.scale[which], rows * sizeof(double)));
+    w.rcap[which] = rows;
+  }
+  return GPC_OK;
+}
+
+template <int S>
+static void launch_slice_t(const double* g, int64_t ld, int kc, int64_t R, int64_t K, const int* emax, int8_t* out,
+                           double* scale, cudaStream_t s) {
+  dim3 grid((unsigned)(R / OZ_SL_ROWS), (unsigned)(K / OZ_BK));
+  oz_slice_kernel<S><<<grid, 256, 0, s>>>(g, ld, kc, R, K, emax, out, scale);
+}
+
+static int slice_operand(OzWorkspace& w, int which, const double* g, int64_t ld, bool kc, int64_t R, int64_t K, int S,
+                         cudaStream_t s, int64_t* launches) {
+  GPC_CHECK(ensure_ws(w, which, (size_t)S * R * K, (size_t)R));
+  GPC_CUDA_CHECK(cudaMemsetAsync(w.emax[which], 0, R * sizeof(int), s));
+  int64_t kchunks = K / 1024;
+  if (kchunks < 1) kchunks = 1;
+  if (kchunks > 16) kchunks = 16;
+  int64_t kchunk = (K + kchunks - 1) / kchunks;
+  dim3 g1((unsigned)(R / 128), (unsigned)kchunks);
+  oz_rowmax_kernel<<<g1, 256, 0, s>>>(g, ld, kc ? 1 : 0, K, kchunk, w.emax[which]);
+  GPC_CUDA_CHECK(cudaGetLastError());
+  switch (S) {
+    case 2: launch_slice_t<2>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
+    case 3: launch_slice_t<3>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
+    case 4: launch_slice_t<4>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
+    case 5: launch_slice_t<5>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
+    case 6: launch_slice_t<6>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
+    case 7: launch_slice_t<7>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
+    default: launch_slice_t<8>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
+  }
+  GPC_CUDA_CHECK(cudaGetLastError());
+  if (launches) (*launches) += 2;
+  if (trace_sync("oz_slice_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
+  return GPC_OK;
+}
+
+int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int slices) {
+  oz_init_settings();
+  int dev = 0;
+  GPC_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) {
+    set_error("launch_gemm_ozaki: device index out of range");
+    return GPC_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(g_oz_mu);
+  OzWorkspace& w = g_oz_ws[dev];
+  const int S = (slices >= 2 && slices <= OZ_MAXS) ? slices : g_oz_S;
+  if (c.m % OZ_BM || c.n % OZ_BN || c.k % OZ_BK || c.k > 32768 || c.C == c.A || c.C == c.B) {
+    set_error("launch_gemm_ozaki: needs m % 128 == n % 64 == k % 128 == 0, k <= 32768 and C distinct from A, B");
+    return GPC_ERR_ARG;
+  }
+  // serialise against the previous Ozaki GEMM (possibly on another stream): the slice buffers are shared
+  if (w.used) GPC_CUDA_CHECK(cudaStreamWaitEvent(s, w.done, 0));
+  const bool same = (c.A == c.B && c.lda == c.ldb && c.a_kc == c.b_kc && c.m == c.n);
+  GPC_CHECK(slice_operand(w, 0, c.A, c.lda, c.a_kc, c.m, c.k, S, s, launches));
+  if (!same) GPC_CHECK(slice_operand(w, 1, c.B, c.ldb, c.b_kc, c.n, c.k, S, s, launches));
+  const int wb = same ? 0 : 1;
+  CUtensorMap tmA, tmB;
+  GPC_CHECK(make_tmap(&tmA, w.sl[0], (int64_t)S * c.m, c.k, OZ_BM));
+  GPC_CHECK(make_tmap(&tmB, w.sl[wb], (int64_t)S * c.n, c.k, OZ_BN));
+  OzArgs a;
+  a.C = c.C;
+  a.ldc = c.ldc;
+  a.scaleA = w.scale[0];
+  a.scaleB = w.scale[wb];
+  a.alpha = c.alpha;
+  a.beta = c.beta;
+  a.tiles_m = (int)(c.m / OZ_BM);
+  a.tiles_n = (int)(c.n / OZ_BN);
+  a.kblocks = (int)(c.k / OZ_BK);
+  a.S = S;
+  const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers, scales*/;
+  int na = (int)((232448 - fixed - 2 * (size_t)S * OZ_B_BYTES) / OZ_A_BYTES);
+  if (na > OZ_MAXNA) na = OZ_MAXNA;
+  a.NA = na;
+  a.lower = c.lower ? 1 : 0;
+  a.ktri = c.ktri ? 1 : 0;
+  a.RpadA = (int)c.m;
+  a.RpadB = (int)c.n;
+  a.errflag = w.errflag;
+  const size_t smem = fixed + 2 * (size_t)S * OZ_B_BYTES + (size_t)na * OZ_A_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    GPC_CUDA_CHECK(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
+  oz_gemm_kernel<<<(unsigned)ntiles, OZ_THREADS, smem, s>>>(tmA, tmB, a);
+  if (launches) (*launches)++;
+  GPC_CUDA_CHECK(cudaGetLastError());
+  GPC_CUDA_CHECK(cudaEventRecord(w.done, s));
+  w.used = true;
+  if (trace_sync("oz_gemm_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
+  return GPC_OK;
+}
+
+void oz_release_device(int dev) {
+  if (dev < 0 || dev >= 64) return;
+  std::lock_guard<std::mutex> lk(g_oz_mu);
+  OzWorkspace& w = g_oz_ws[dev];
+  for (int i = 0; i < 2; i++) {
+    if (w.sl[i]) cudaFree(w.sl[i]);
+    if (w.emax[i]) cudaFree(w.emax[i]);
+    if (w.scale[i]) cudaFree(w.scale[i]);
+  }
+  if (w.errflag) cudaFree(w.errflag);
+  if (w.done) cudaEventDestroy(w.done);
+  w = OzWorkspace();
+}
+
+}  // namespace gpc
+
+extern "C" int gpc_oz_slice_check(int device, int64_t R, int64_t K, int kc, int S, const double* X, signed char* slices_out,
+                                  double* scale_out) {
+  using namespace gpc;
+  if (R % 128 || K % 128 || R < 128 || K < 128 || S < 2 || S > OZ_MAXS || !X || !slices_out || !scale_out) {
+    set_error("gpc_oz_slice_check: R, K multiples of 128, S in 2..8");
+    return GPC_ERR_ARG;
+  }
+  GPC_CUDA_CHECK(cudaSetDevice(device));
+  double* dX = nullptr;
+  OzWorkspace w;
+  cudaStream_t s;
+  GPC_CUDA_CHECK(cudaStreamCreate(&s));
+  GPC_CUDA_CHECK(cudaMalloc(&dX, (size_t)R * K * sizeof(double)));
+  GPC_CUDA_CHECK(cudaMemcpy(dX, X, (size_t)R * K * sizeof(double), cudaMemcpyHostToDevice));
+  int rc = slice_operand(w, 0, dX, kc ? K : R, kc != 0, R, K, S, s, nullptr);
+  if (rc == GPC_OK) {
+    GPC_CUDA_CHECK(cudaStreamSynchronize(s));
+    GPC_CUDA_CHECK(cudaMemcpy(slices_out, w.sl[0], (size_t)S * R * K, cudaMemcpyDeviceToHost));
+    GPC_CUDA_CHECK(cudaMemcpy(scale_out, w.scale[0], (size_t)R * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  cudaFree(dX);
+  cudaFree(w.sl[0]);
+  cudaFree(w.emax[0]);
+  cudaFree(w.scale[0]);
+  cudaFree(w.errflag);
+  if (w.done) cudaEventDestroy(w.done);
+  cudaStreamDestroy(s);
+  return rc;
+}
