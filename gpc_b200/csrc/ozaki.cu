@@ -244,6 +244,56 @@ struct OzArgs {
   int* errflag;
 };
 
+__device__ __forceinline__ uint32_t oz_elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred;
+}
+// descriptor = constant high word (SBO 1024 B, version 1, 128B swizzle) | low word (start address >> 4, LBO 1)
+constexpr uint32_t OZ_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t oz_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void oz_mma_i8_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(OZ_DESC_HI)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t oz_idesc_c(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+}
+
+// all MMAs of one A slice (p) against its B slices for one k-block: 4 k-steps x ceil((S-p)/4) instructions
+template <int S, int P>
+__device__ __forceinline__ void oz_issue_slice(uint32_t tmem, uint32_t a_lo, uint32_t b_lo, uint32_t first_acc) {
+#pragma unroll
+  for (int ks = 0; ks < OZ_BK / OZ_UK; ks++) {
+#pragma unroll
+    for (int q0 = 0; q0 < S - P; q0 += 4) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int nq = (S - P - q0) < 4 ? (S - P - q0) : 4;
+      const uint32_t acc = (P == 0 && ks == 0) ? first_acc : 1u;  // A slice 0 touches every level first
+      oz_mma_i8_lo(tmem + (uint32_t)(P + q0) * OZ_BN, a_lo + ks * (OZ_UK >> 4), b_lo + q0 * (OZ_B_BYTES >> 4) + ks * (OZ_UK >> 4),
+                   oz_idesc_c(nq * OZ_BN), acc);
+    }
+  }
+}
+
+template <int S, int NA>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzArgs a) {
   extern __shared__ uint8_t oz_smem_raw[];
@@ -261,7 +311,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   }
   if (a.lower && bn > 2 * bm + 1) return;  // whole CTA, before any barrier / TMEM allocation
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int S = a.S, NA = a.NA;
   const int m0 = bm * OZ_BM, n0 = bn * OZ_BN;
   const int kb0 = a.ktri ? (m0 / OZ_BK) : 0;
   const int KB = a.kblocks;
@@ -277,10 +326,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   double* s_cscale = reinterpret_cast<double*>(tail + 256);   // 64 doubles
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tail + 256 + 512);
   const uint32_t bar0 = smem_u32(bars);
-  auto FULL_A = [&](int i) { return bar0 + 8u * i; };
-  auto EMPTY_A = [&](int i) { return bar0 + 8u * (OZ_MAXNA + i); };
-  auto FULL_B = [&](int i) { return bar0 + 8u * (2 * OZ_MAXNA + i); };
-  auto EMPTY_B = [&](int i) { return bar0 + 8u * (2 * OZ_MAXNA + 2 + i); };
+  auto FULL_A = [&](uint32_t i) { return bar0 + 8u * i; };
+  auto EMPTY_A = [&](uint32_t i) { return bar0 + 8u * (OZ_MAXNA + i); };
+  auto FULL_B = [&](uint32_t i) { return bar0 + 8u * (2 * OZ_MAXNA + i); };
+  auto EMPTY_B = [&](uint32_t i) { return bar0 + 8u * (2 * OZ_MAXNA + 2 + i); };
   const uint32_t TMEM_FULL = bar0 + 8u * (2 * OZ_MAXNA + 4);
 
   if (warp == 4 && lane == 0) {
@@ -311,53 +360,56 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   if (warp == 4) {
     if (lane == 0) {
       // ===== TMA producer =====
-      uint32_t ia = 0;
+      uint32_t slot = 0, round = 0;
       for (int kb = kb0; kb < KB; kb++) {
         const int it = kb - kb0, set = it & 1;
         if (it >= 2) oz_mbar_wait(EMPTY_B(set), ((it >> 1) - 1) & 1, a.errflag, 1);
         oz_mbar_expect_tx(FULL_B(set), (uint32_t)S * OZ_B_BYTES);
+#pragma unroll
         for (int q = 0; q < S; q++)
           oz_tma_load_2d(sB + (uint32_t)(set * S + q) * OZ_B_BYTES, &tmB, FULL_B(set), kb * OZ_BK, q * a.RpadB + n0);
-        for (int p = 0; p < S; p++, ia++) {
-          const uint32_t slot = ia % NA, round = ia / NA;
+#pragma unroll
+        for (int p = 0; p < S; p++) {
           if (round >= 1) oz_mbar_wait(EMPTY_A(slot), (round - 1) & 1, a.errflag, 2);
           oz_mbar_expect_tx(FULL_A(slot), OZ_A_BYTES);
           oz_tma_load_2d(sA + slot * OZ_A_BYTES, &tmA, FULL_A(slot), kb * OZ_BK, p * a.RpadA + m0);
+          if (++slot == NA) {
+            slot = 0;
+            round++;
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      uint32_t ia = 0;
-      for (int kb = kb0; kb < KB; kb++) {
-        const int it = kb - kb0, set = it & 1;
-        oz_mbar_wait(FULL_B(set), (it >> 1) & 1, a.errflag, 3);
-        oz_tc_fence_after();
-        const uint32_t b_base = sB + (uint32_t)(set * S) * OZ_B_BYTES;
-        for (int p = 0; p < S; p++, ia++) {
-          const uint32_t slot = ia % NA, round = ia / NA;
-          oz_mbar_wait(FULL_A(slot), round & 1, a.errflag, 4);
-          oz_tc_fence_after();
-          const uint32_t a_base = sA + slot * OZ_A_BYTES;
-          const int cnt = S - p;  // B slices q = 0..cnt-1 pair with A slice p; level = p + q
-#pragma unroll
-          for (int ks = 0; ks < OZ_BK / OZ_UK; ks++) {
-            const uint64_t adesc = oz_smem_desc(a_base + ks * OZ_UK);
-            for (int q0 = 0; q0 < cnt; q0 += 4) {
-              const int nq = (cnt - q0) < 4 ? (cnt - q0) : 4;
-              const uint64_t bdesc = oz_smem_desc(b_base + (uint32_t)q0 * OZ_B_BYTES + ks * OZ_UK);
-              const uint32_t acc = (it == 0 && ks == 0 && p == 0) ? 0u : 1u;  // A slice 0 touches every level first
-              oz_mma_i8(tmem + (uint32_t)(p + q0) * OZ_BN, adesc, bdesc, oz_idesc(nq * OZ_BN), acc);
-            }
-          }
-          oz_tc_commit(EMPTY_A(slot));
-        }
-        oz_tc_commit(EMPTY_B(set));
-      }
-      oz_tc_commit(TMEM_FULL);
+    // ===== MMA issuer: the whole warp walks the pipeline, one elected lane issues (keeps UTCIMMA in uniform control flow)
+    uint32_t slot = 0, aphase = 0;
+    const uint32_t a_lo0 = oz_desc_lo(sA), b_lo0 = oz_desc_lo(sB);
+    for (int kb = kb0; kb < KB; kb++) {
+      const int it = kb - kb0, set = it & 1;
+      oz_mbar_wait(FULL_B(set), (it >> 1) & 1, a.errflag, 3);
+      const uint32_t b_lo = b_lo0 + (uint32_t)set * (S * OZ_B_BYTES >> 4);
+      const uint32_t first_acc = it == 0 ? 0u : 1u;
+#define OZ_SLICE(P)                                                            \
+  if (P < S) {                                                                 \
+    oz_mbar_wait(FULL_A(slot), aphase, a.errflag, 4);                          \
+    oz_tc_fence_after();                                                       \
+    if (oz_elect_one()) {                                                      \
+      oz_issue_slice<S, (P < S ? P : 0)>(tmem, a_lo0 + slot * (OZ_A_BYTES >> 4), b_lo, first_acc); \
+      oz_tc_commit(EMPTY_A(slot));                                             \
+    }                                                                          \
+    __syncwarp();                                                              \
+    if (++slot == NA) {                                                        \
+      slot = 0;                                                                \
+      aphase ^= 1;                                                             \
+    }                                                                          \
+  }
+      OZ_SLICE(0) OZ_SLICE(1) OZ_SLICE(2) OZ_SLICE(3) OZ_SLICE(4) OZ_SLICE(5) OZ_SLICE(6) OZ_SLICE(7)
+#undef OZ_SLICE
+      if (oz_elect_one()) oz_tc_commit(EMPTY_B(set));
+      __syncwarp();
     }
+    if (oz_elect_one()) oz_tc_commit(TMEM_FULL);
     __syncwarp();
   } else {
     // ===== epilogue warps 0..3: TMEM lane = output row =====
@@ -366,7 +418,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     const int row = warp * 32 + lane;
     const double rs = a.scaleA[m0 + row] * (1.0 / 4096.0);  // 2^-12: weight of level c = 2
     const double alpha = a.alpha, beta = a.beta;
-    oz_mbar_wait(TMEM_FULL, 0, a.errflag, 5);
+    while (!oz_mbar_try_wait(TMEM_FULL, 0)) __nanosleep(256);  // stay out of the issuer's way while the tile is computed
     oz_tc_fence_after();
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     double* crow = a.C + (int64_t)(m0 + row) + (int64_t)n0 * a.ldc;
@@ -377,6 +429,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       oz_tmem_ld16(trow + (uint32_t)((S - 1) * OZ_BN + ch * 16), r);
 #pragma unroll
       for (int j = 0; j < 16; j++) acc[j] = (double)r[j];
+#pragma unroll
       for (int l = S - 2; l >= 0; l--) {
         oz_tmem_ld16(trow + (uint32_t)(l * OZ_BN + ch * 16), r);
 #pragma unroll
@@ -402,6 +455,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
+constexpr size_t OZ_SMEM_FIXED = 1024 /*alignment slack*/ + 1024 /*barriers, column scales, TMEM address*/;
+constexpr int oz_na(int S) {
+  return (int)((232448 - OZ_SMEM_FIXED - 2 * (size_t)S * OZ_B_BYTES) / OZ_A_BYTES) > OZ_MAXNA
+             ? OZ_MAXNA
+             : (int)((232448 - OZ_SMEM_FIXED - 2 * (size_t)S * OZ_B_BYTES) / OZ_A_BYTES);
+}
+constexpr size_t oz_smem(int S) { return OZ_SMEM_FIXED + 2 * (size_t)S * OZ_B_BYTES + (size_t)oz_na(S) * OZ_A_BYTES; }
+
 typedef CUresult (*PFN_tmap_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -578,23 +639,30 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   a.tiles_n = (int)(c.n / OZ_BN);
   a.kblocks = (int)(c.k / OZ_BK);
   a.S = S;
-  const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers, scales*/;
-  int na = (int)((232448 - fixed - 2 * (size_t)S * OZ_B_BYTES) / OZ_A_BYTES);
-  if (na > OZ_MAXNA) na = OZ_MAXNA;
-  a.NA = na;
+  a.NA = oz_na(S);
   a.lower = c.lower ? 1 : 0;
   a.ktri = c.ktri ? 1 : 0;
   a.RpadA = (int)c.m;
   a.RpadB = (int)c.n;
   a.errflag = w.errflag;
-  const size_t smem = fixed + 2 * (size_t)S * OZ_B_BYTES + (size_t)na * OZ_A_BYTES;
-  static bool configured = false;
-  if (!configured) {
-    GPC_CUDA_CHECK(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    configured = true;
-  }
   const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
-  oz_gemm_kernel<<<(unsigned)ntiles, OZ_THREADS, smem, s>>>(tmA, tmB, a);
+  switch (S) {
+#define OZ_CASE(SS)                                                                                              \
+  case SS: {                                                                                                     \
+    static bool configured = false;                                                                              \
+    auto kern = oz_gemm_kernel<SS, oz_na(SS)>;                                                                   \
+    if (!configured) {                                                                                           \
+      GPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem(SS))); \
+      configured = true;                                                                                         \
+    }                                                                                                            \
+    kern<<<(unsigned)ntiles, OZ_THREADS, oz_smem(SS), s>>>(tmA, tmB, a);                                         \
+  } break;
+    OZ_CASE(2) OZ_CASE(3) OZ_CASE(4) OZ_CASE(5) OZ_CASE(6) OZ_CASE(7) OZ_CASE(8)
+#undef OZ_CASE
+    default:
+      set_error("launch_gemm_ozaki: slices out of range");
+      return GPC_ERR_ARG;
+  }
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
   GPC_CUDA_CHECK(cudaEventRecord(w.done, s));
