@@ -53,6 +53,8 @@ static int gemm(const Dense& d, const GemmCall& g) {
   p->used += 2;
   double fl = g.lower ? (double)g.m * (double)(g.m + TILE) * (double)g.k : 2.0 * (double)g.m * (double)g.n * (double)g.k;
   p->flops.push_back(fl);
+  const bool inplace = (g.C == g.A || g.C == g.B);
+  p->recs.push_back({g.m, g.n, g.k, g.lower ? 1 : 0, (!inplace && oz_wants(g)) ? 1 : 0});
   return rc;
 }
 
@@ -217,6 +219,7 @@ struct gpc_ctx {
   GemmProf* prof;       // non-null in profiling mode
   double prof_ms, prof_flops;
   int64_t prof_count;
+  double prof_split[8];  // DMMA [ms, flops, launches, 0], Ozaki [ms, fp64-equivalent flops, launches, int8 ops]
 };
 
 static const int SC_LOGDET = 0, SC_QUAD = 1, SC_TRACE = 2, SC_G = 8;
@@ -777,6 +780,7 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
     if (c->prof) {
       c->prof->used = 0;
       c->prof->flops.clear();
+      c->prof->recs.clear();
     }
     GPC_CHECK(potrf_async(c));
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[2], s));
@@ -823,14 +827,29 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
     c->prof_ms = 0.0;
     c->prof_flops = 0.0;
     c->prof_count = (int64_t)(c->prof->used / 2);
+    for (int q = 0; q < 8; q++) c->prof_split[q] = 0.0;
+    const char* dump = getenv("GPC_PROF_DUMP");
+    FILE* df = dump ? fopen(dump, "w") : nullptr;
+    if (df) fprintf(df, "m,n,k,lower,engine,ms,flops\n");
+    const double S = (double)oz_slices();
     for (size_t i = 0; i + 1 < c->prof->used; i += 2) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, c->prof->ev[i], c->prof->ev[i + 1]);
       c->prof_ms += ms;
       c->prof_flops += c->prof->flops[i / 2];
+      const GemmProf::Rec& r = c->prof->recs[i / 2];
+      const int o = r.ozaki ? 4 : 0;  // [ms, flops, count, int8 ops] per engine
+      c->prof_split[o + 0] += ms;
+      c->prof_split[o + 1] += c->prof->flops[i / 2];
+      c->prof_split[o + 2] += 1.0;
+      if (r.ozaki) c->prof_split[o + 3] += c->prof->flops[i / 2] * S * (S + 1.0) / 2.0;
+      if (df) fprintf(df, "%lld,%lld,%lld,%d,%s,%.6f,%.0f\n", (long long)r.m, (long long)r.n, (long long)r.k, r.lower,
+                      r.ozaki ? "ozaki" : "dmma", ms, c->prof->flops[i / 2]);
     }
+    if (df) fclose(df);
     c->prof->used = 0;
     c->prof->flops.clear();
+    c->prof->recs.clear();
   }
   for (int i = 0; i < 5; i++) {
     float ms = 0.f;
@@ -858,6 +877,12 @@ int gpc_last_gemm_profile(gpc_ctx* c, double* total_ms, int64_t* count, double* 
   if (total_ms) *total_ms = c->prof_ms;
   if (count) *count = c->prof_count;
   if (flops) *flops = c->prof_flops;
+  return GPC_OK;
+}
+
+int gpc_last_gemm_profile_split(gpc_ctx* c, double* out8) {
+  if (!c || !out8) return GPC_ERR_ARG;
+  for (int q = 0; q < 8; q++) out8[q] = c->prof_split[q];
   return GPC_OK;
 }
 

@@ -61,7 +61,8 @@ void gemm_force_config(int cfg);  // -1: heuristic (default); 0..4: force a DMMA
 // on < 0 / slices == 0 / min_* <= 0 leave the respective setting unchanged.  Defaults come from the environment:
 // GPC_OZAKI (0/1), GPC_OZAKI_SLICES (2..8), GPC_OZAKI_MIN_MN, GPC_OZAKI_MIN_K.
 void oz_configure(int on, int slices, int64_t min_mn, int64_t min_k);
-bool oz_wants(const GemmCall& g);  // true when launch_gemm should route this call to launch_gemm_ozaki
+bool oz_wants(const GemmCall& g);
+int oz_slices();                  // configured number of slices  // true when launch_gemm should route this call to launch_gemm_ozaki
 int launch_gemm_ozaki(const GemmCall& g, cudaStream_t s, int64_t* launches, int slices = 0);  // 0: configured
 void oz_release_device(int dev);   // frees the per-device slice workspace
 
@@ -94,6 +95,8 @@ int launch_trtri_leaf(const double* A, int64_t lda, double* Dinv, cudaStream_t s
 struct GemmProf {  // optional per-launch timing of the DMMA GEMM kernel (bench.py roofline)
   std::vector<cudaEvent_t> ev;  // pairs
   std::vector<double> flops;    // executed flops of each launch
+  struct Rec { int64_t m, n, k; int lower, ozaki; };
+  std::vector<Rec> recs;        // shape and engine of each launch
   size_t used = 0;
 };
 struct Fork {  // side streams + events for fork/join concurrency inside the recursions (owned by the context)

@@ -24,6 +24,8 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
+#include <map>
 #include <mutex>
 #include "common.cuh"
 
@@ -424,8 +426,18 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     double* crow = a.C + (int64_t)(m0 + row) + (int64_t)n0 * a.ldc;
 #pragma unroll 1
     for (int ch = 0; ch < OZ_BN / 16; ch++) {
-      double acc[16];
+      double acc[16], cv[16];
       int r[16];
+      double* cp = crow + (int64_t)(ch * 16) * a.ldc;
+      // all C loads of the chunk first (independent, in flight while the levels are combined): a load placed after the
+      // previous column's store could not be hoisted above it (possible aliasing) and would serialise 64 round trips
+      if (beta != 0.0) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) cv[j] = __ldcg(cp + (int64_t)j * a.ldc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) cv[j] = 0.0;
+      }
       oz_tmem_ld16(trow + (uint32_t)((S - 1) * OZ_BN + ch * 16), r);
 #pragma unroll
       for (int j = 0; j < 16; j++) acc[j] = (double)r[j];
@@ -437,10 +449,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       }
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        double v = alpha * (acc[j] * rs * s_cscale[ch * 16 + j]);
-        double* p = crow + (int64_t)(ch * 16 + j) * a.ldc;
-        if (beta != 0.0) v = fma(beta, *p, v);
-        *p = v;
+        const double v = alpha * (acc[j] * rs * s_cscale[ch * 16 + j]);
+        cp[(int64_t)j * a.ldc] = fma(beta, cv[j], v);
       }
     }
   }
@@ -514,16 +524,26 @@ struct OzWorkspace {
 };
 static std::mutex g_oz_mu;
 static OzWorkspace g_oz_ws[64];
+// Calls whose slices fit OZ_SMALL_BYTES per operand take one of OZ_POOL fixed-size workspaces round-robin instead (each
+// guarded by its own event), so that the concurrent branches of the recursions (fork/join side streams) do not
+// serialise on the shared buffers.  The pool is allocated once per device: no allocation in steady state.
+constexpr size_t OZ_SMALL_BYTES = (size_t)16 << 20;
+constexpr size_t OZ_SMALL_ROWS = 32768;  // S*R*K <= 16 MB with K >= 128, S >= 2
+constexpr int OZ_POOL = 8;
+static OzWorkspace g_oz_pool[64][OZ_POOL];
+static unsigned g_oz_pool_next[64];
 
 static int g_oz_on = -1, g_oz_S = 8;
-static int64_t g_oz_min_mn = 1024, g_oz_min_k = 1024;
+static int64_t g_oz_min_mn = 256, g_oz_min_k = 512;
+static double g_oz_bias = 1.0;  // use the tensor-core engine when its modelled time is below bias x the DMMA time
 static void oz_init_settings() {
   if (g_oz_on >= 0) return;
   const char* e = getenv("GPC_OZAKI");
-  g_oz_on = e ? atoi(e) : 0;
+  g_oz_on = e ? atoi(e) : 1;
   if ((e = getenv("GPC_OZAKI_SLICES"))) g_oz_S = atoi(e);
   if ((e = getenv("GPC_OZAKI_MIN_MN"))) g_oz_min_mn = atoll(e);
   if ((e = getenv("GPC_OZAKI_MIN_K"))) g_oz_min_k = atoll(e);
+  if ((e = getenv("GPC_OZAKI_BIAS"))) g_oz_bias = atof(e);
   if (g_oz_S < 2) g_oz_S = 2;
   if (g_oz_S > OZ_MAXS) g_oz_S = OZ_MAXS;
 }
@@ -534,6 +554,29 @@ void oz_configure(int on, int slices, int64_t min_mn, int64_t min_k) {
   if (min_mn > 0) g_oz_min_mn = min_mn;
   if (min_k > 0) g_oz_min_k = min_k;
 }
+// Engine choice per call: a wave-quantised cost model of both engines, calibrated on B200 (tools/oz_check.py perf,
+// tools/oz_sweep.py): Ozaki = fixed launch cost + slicing traffic + waves of 128x64 tiles at 36 int8 MMAs per fp64 MMA;
+// DMMA = waves of 64x64 tiles (small problems) or the measured large-problem rate.
+static double oz_cost_us(const GemmCall& c, int S) {
+  const double tm = (double)(c.m / OZ_BM), tn = (double)(c.n / OZ_BN);
+  const double tiles = c.lower ? tm * (tm + 1.0) : tm * tn;  // lower: row block bm owns 2(bm+1) column tiles
+  const double waves = ceil(tiles / 148.0);
+  const bool same = (c.A == c.B && c.lda == c.ldb && c.a_kc == c.b_kc && c.m == c.n);
+  const double elems = (double)c.k * (same ? (double)c.m : (double)(c.m + c.n));
+  const double per_k = 0.0267 * (S * (S + 1)) / 72.0;  // us per unit of k per tile wave (S = 8 measured)
+  return 20.0 + elems * (16.0 + S) / 3.0e6 + waves * ((double)c.k * per_k + 5.0);
+}
+static double dmma_cost_us(const GemmCall& c) {
+  const double flops = c.lower ? (double)c.m * (double)(c.m + TILE) * (double)c.k : 2.0 * (double)c.m * (double)c.n * (double)c.k;
+  const double t64 = c.lower ? (double)(c.m / 64) * (double)(c.m / 64 + 1) / 2.0 : (double)(c.m / 64) * (double)(c.n / 64);
+  const double big = flops / 33.0e6;                                   // 33 TFLOP/s sustained on many-wave problems
+  const double small = ceil(t64 / 296.0) * (double)c.k * 0.0655;      // 64x64 tiles, 2 CTAs per SM
+  return 4.0 + (big > small ? big : small);
+}
+int oz_slices() {
+  oz_init_settings();
+  return g_oz_S;
+}
 bool oz_wants(const GemmCall& c) {
   oz_init_settings();
   if (!g_oz_on) return false;
@@ -542,7 +585,7 @@ bool oz_wants(const GemmCall& c) {
   if (c.m < g_oz_min_mn || c.n < g_oz_min_mn || c.k < g_oz_min_k) return false;
   if (c.k > 32768) return false;  // int32 level accumulators: (S) * k * 64^2 < 2^31
   if (c.m * (int64_t)OZ_MAXS >= (1LL << 31) || c.n * (int64_t)OZ_MAXS >= (1LL << 31)) return false;
-  return true;
+  return oz_cost_us(c, g_oz_S) < g_oz_bias * dmma_cost_us(c);
 }
 
 static int ensure_ws(OzWorkspace& w, int which, size_t bytes, size_t rows) {
@@ -582,9 +625,10 @@ static int slice_operand(OzWorkspace& w, int which, const double* g, int64_t ld,
                          cudaStream_t s, int64_t* launches) {
   GPC_CHECK(ensure_ws(w, which, (size_t)S * R * K, (size_t)R));
   GPC_CUDA_CHECK(cudaMemsetAsync(w.emax[which], 0, R * sizeof(int), s));
-  int64_t kchunks = K / 1024;
+  // enough blocks to cover the GPU a few times: (R/128) x kchunks >= ~600, chunks of >= 64 columns
+  int64_t kchunks = (600 + R / 128 - 1) / (R / 128);
+  if (kchunks > K / 64) kchunks = K / 64;
   if (kchunks < 1) kchunks = 1;
-  if (kchunks > 16) kchunks = 16;
   int64_t kchunk = (K + kchunks - 1) / kchunks;
   dim3 g1((unsigned)(R / 128), (unsigned)kchunks);
   oz_rowmax_kernel<<<g1, 256, 0, s>>>(g, ld, kc ? 1 : 0, K, kchunk, w.emax[which]);
@@ -613,8 +657,13 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
     return GPC_ERR_ARG;
   }
   std::lock_guard<std::mutex> lk(g_oz_mu);
-  OzWorkspace& w = g_oz_ws[dev];
   const int S = (slices >= 2 && slices <= OZ_MAXS) ? slices : g_oz_S;
+  const size_t op_bytes = (size_t)S * (size_t)(c.m > c.n ? c.m : c.n) * (size_t)c.k;
+  const bool shared_ws = op_bytes > OZ_SMALL_BYTES;
+  OzWorkspace& w = shared_ws ? g_oz_ws[dev] : g_oz_pool[dev][g_oz_pool_next[dev]++ % OZ_POOL];
+  if (!shared_ws && !w.sl[0]) {
+    for (int i = 0; i < 2; i++) GPC_CHECK(ensure_ws(w, i, OZ_SMALL_BYTES, OZ_SMALL_ROWS));
+  }
   if (c.m % OZ_BM || c.n % OZ_BN || c.k % OZ_BK || c.k > 32768 || c.C == c.A || c.C == c.B) {
     set_error("launch_gemm_ozaki: needs m % 128 == n % 64 == k % 128 == 0, k <= 32768 and C distinct from A, B");
     return GPC_ERR_ARG;
@@ -683,6 +732,17 @@ void oz_release_device(int dev) {
   if (w.errflag) cudaFree(w.errflag);
   if (w.done) cudaEventDestroy(w.done);
   w = OzWorkspace();
+  for (int q = 0; q < OZ_POOL; q++) {
+    OzWorkspace& v = g_oz_pool[dev][q];
+    for (int i = 0; i < 2; i++) {
+      if (v.sl[i]) cudaFree(v.sl[i]);
+      if (v.emax[i]) cudaFree(v.emax[i]);
+      if (v.scale[i]) cudaFree(v.scale[i]);
+    }
+    if (v.errflag) cudaFree(v.errflag);
+    if (v.done) cudaEventDestroy(v.done);
+    v = OzWorkspace();
+  }
 }
 
 }  // namespace gpc

@@ -147,6 +147,9 @@ int gpc_last_timings(gpc_ctx* ctx, double* ms6);
  * stream; after an evaluation gpc_last_gemm_profile reports the summed kernel time, launch count and executed flops */
 int gpc_ctx_set_profile(gpc_ctx* ctx, int on);
 int gpc_last_gemm_profile(gpc_ctx* ctx, double* total_ms, int64_t* count, double* flops);
+/* the same split by engine: out8 = DMMA [ms, flops, launches, 0], Ozaki [ms, fp64-equivalent flops, launches, int8 ops
+ * executed].  With GPC_PROF_DUMP=<file> in the environment every profiled GEMM is also written there (shape, engine, ms). */
+int gpc_last_gemm_profile_split(gpc_ctx* ctx, double* out8);
 
 /* ---- CMatrix level: drop-ins for the lapack.h calls CMatrix makes (host pointers, LAPACK argument meaning,
  *      scalars by value, 64-bit dimensions).  Each stages through device memory. ---------------------------*/
