@@ -10,8 +10,9 @@ K build -> Cholesky (jitChol) -> K^-1 -> alpha -> log-likelihood terms -> hyper-
   value : evaluations/s with X and m resident in HBM (only theta changes per step)
   e2e   : the same through the public call with HOST buffers: every step uploads X and m from pinned host memory
           and reads ll terms + gradient back
-  roofline : the dominant kernel (DMMA GEMM/SYRK engine) -- algorithmic N^3 flop of potrf+inverse per evaluation over
-          the summed CUDA-event duration of its launches, against the measured register-resident DMMA peak
+  roofline : the dominant kernel -- oz_gemm_kernel, the tcgen05 int8 tensor-core GEMM that carries the fp64 flops of
+          potrf + inverse (N^3 per evaluation) as 8 int8 slices: algorithmic fp64 flops of its calls over their summed
+          CUDA-event duration, against the fp64-equivalent peak of the int8 pipe (2 x measured bf16 peak / 36)
   cpu_baseline / --impl reference : the unmodified reference (oracle/_ref) on this box's host cores, same inputs
 Multi-GPU (round 1): the path does not shard at this size -- ranks run independent replicas (one theta candidate
 each), no data-path collective; "scaling": "weak".
@@ -251,32 +252,72 @@ def main():
     clocks = sampler.stop() if rank == 0 else {}
     ll = -0.5 * (out[1] + out[0]) - N * 0.5 * np.log(2 * np.pi)
 
-    # ---- roofline of the dominant kernel: DMMA GEMM/SYRK launches of one evaluation, CUDA events per launch
+    # ---- roofline of the dominant kernel.  Every GEMM/SYRK call of one evaluation is bracketed by CUDA events on the
+    #      context's stream (profiling mode, calls serialised) and attributed to its engine:
+    #        ozaki : oz_gemm_kernel (+ its slicing kernels) -- tcgen05.mma.kind::i8, S(S+1)/2 int8 MMAs per fp64 MMA
+    #        dmma  : dgemm_kernel -- mma.sync.m8n8k4.f64
+    #      The dominant one (by time) is reported: achieved = ALGORITHMIC fp64 flops of its calls / their summed duration.
     check(lib().gpc_ctx_set_profile(ctx.handle, 1))
     one_eval(300, False)
     gms, cnt, gfl = C.c_double(0), C.c_int64(0), C.c_double(0)
     check(lib().gpc_last_gemm_profile(ctx.handle, C.byref(gms), C.byref(cnt), C.byref(gfl)))
+    split = np.zeros(8)
+    check(lib().gpc_last_gemm_profile_split(ctx.handle, ptr(split)))
     check(lib().gpc_ctx_set_profile(ctx.handle, 0))
     peak = C.c_double(0)
     check(lib().gpc_bench_dmma_peak(local_rank, C.byref(peak)))
     alg_flops = float(N) ** 3  # potrf N^3/3 + inverse 2N^3/3
-    achieved = alg_flops / (gms.value * 1e-3) / 1e12 if gms.value > 0 else 0.0
+    S = 8
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tfile):
         try:
-            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tfile))
         except Exception:
             traffic = None
-    roofline = {
-        "bound": "tensor", "kernel": "dgemm_kernel (mma.sync m8n8k4 f64 = DMMA.8x8x4)", "achieved": achieved,
-        "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": traffic,
-        "peak_source": "measured on this GPU by gpc_bench_dmma_peak (register-resident DMMA loop, burst); "
-                       "MEASURED_PEAKS.json has no fp64 figure",
-        "launches_per_eval": int(cnt.value), "kernel_ms_per_eval": gms.value,
-        "algorithmic_flops_per_eval": alg_flops, "executed_flops_per_eval": gfl.value,
-        "share_of_step": gms.value / (ms_dev / args.steps) if ms_dev > 0 else None,
+    mp = {}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = float(mp.get("bf16_tflops", 1590.0))
+    bf16_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in mp else "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
+    dm_ms, dm_fl, dm_n = split[0], split[1], int(split[2])
+    oz_ms, oz_fl, oz_n, oz_ops = split[4], split[5], int(split[6]), split[7]
+    engines = {
+        "ozaki": {"calls": oz_n, "ms": oz_ms, "fp64_flops": oz_fl, "fp64_equiv_tflops": oz_fl / (oz_ms * 1e-3) / 1e12 if oz_ms else 0.0,
+                  "int8_tops": oz_ops / (oz_ms * 1e-3) / 1e12 if oz_ms else 0.0},
+        "dmma": {"calls": dm_n, "ms": dm_ms, "fp64_flops": dm_fl, "tflops": dm_fl / (dm_ms * 1e-3) / 1e12 if dm_ms else 0.0,
+                 "peak_tflops": peak.value},
     }
+    if oz_ms >= dm_ms and oz_ms > 0:
+        # fp64-equivalent peak of the int8 pipe: int8 runs at twice the bf16 rate on sm_100a, one fp64 MMA costs
+        # S(S+1)/2 = 36 int8 MMAs (S = 8 slices)
+        pk = 2.0 * bf16 / (S * (S + 1) / 2.0)
+        ach = oz_fl / (oz_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma.kind::i8 + TMEM + TMA; fp64 via 8 int8 slices) incl. slicing",
+            "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+            "traffic": (traffic or {}).get("oz_gemm_kernel"),
+            "peak_source": "fp64-equivalent of the int8 tensor pipe: 2 x %s = %.0f TOP/s, / 36 int8 MMAs per fp64 MMA; "
+                           "of measured" % (bf16_src, 2.0 * bf16),
+            "launches_per_eval": oz_n, "kernel_ms_per_eval": oz_ms, "algorithmic_flops": oz_fl,
+            "share_of_step": oz_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
+        }
+    else:
+        ach = dm_fl / (dm_ms * 1e-3) / 1e12 if dm_ms else 0.0
+        roofline = {
+            "bound": "tensor", "kernel": "dgemm_kernel (mma.sync m8n8k4 f64 = DMMA.8x8x4)", "achieved": ach,
+            "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value if peak.value else None,
+            "traffic": (traffic or {}).get("dgemm_kernel"),
+            "peak_source": "measured on this GPU by gpc_bench_dmma_peak (register-resident DMMA loop, burst); "
+                           "MEASURED_PEAKS.json has no fp64 figure",
+            "launches_per_eval": dm_n, "kernel_ms_per_eval": dm_ms, "algorithmic_flops": dm_fl,
+            "share_of_step": dm_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
+        }
+    roofline["engines"] = engines
+    roofline["algorithmic_flops_per_eval"] = alg_flops
+    roofline["gemm_ms_per_eval_serialised"] = gms.value
 
     # ---- extra: C3 (N=32768, rbfard) single-GPU timing, the north-star "<1 s" target
     also = None

@@ -52,6 +52,8 @@ static int gemm(const Dense& d, const GemmCall& g) {
   GPC_CUDA_CHECK(cudaEventRecord(p->ev[p->used + 1], d.s));
   p->used += 2;
   double fl = g.lower ? (double)g.m * (double)(g.m + TILE) * (double)g.k : 2.0 * (double)g.m * (double)g.n * (double)g.k;
+  // triangular operand: the zero k range is skipped (lower + triangular = the W'W product of the inverse, n^3/3)
+  if (g.ktri || g.a_tri || g.b_tri) fl = g.lower ? (double)g.m * (double)g.m * (double)g.k / 3.0 : 0.5 * fl;
   p->flops.push_back(fl);
   const bool inplace = (g.C == g.A || g.C == g.B);
   p->recs.push_back({g.m, g.n, g.k, g.lower ? 1 : 0, (!inplace && oz_wants(g)) ? 1 : 0});
@@ -185,6 +187,93 @@ int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* O
   return launch_transpose(Out + n1, ldo, Out + n1 * ldo, ldo, n2, n1, d.s, d.launches);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Factor + explicit triangular inverse.  W = L^-1 is built alongside L, so every panel solve is ONE large GEMM
+// (L21 = A21 W11', triangular k-range skipped) instead of a recursion down to TILE-wide in-place leaves, and the
+// inverse (K^-1 = W'W) is ONE triangular product.  Same flop count as dpotrf_ + dpotri_ (N^3/3 + 2N^3/3,
+// reference lapack.h:59-73), but all of it in calls large enough for the tensor-core engine.
+//   node(A, n):  node(A11) -> L11, W11
+//                L21 = A21 W11'                 (main stream, via tmpL: the product cannot be formed in place)
+//                T   = L21 W11                  (side stream, needed only for W21)
+//                A22 -= L21 L21'                (SYRK)
+//                node(A22) -> L22, W22
+//                W21 = -W22 T
+// ------------------------------------------------------------------------------------------------------
+size_t potrf_inv_tspace(int64_t n) {
+  if (n <= TILE) return 0;
+  int64_t n1 = split(n), n2 = n - n1;
+  size_t a = potrf_inv_tspace(n1), b = (size_t)n1 * n2 + potrf_inv_tspace(n2);
+  return a > b ? a : b;
+}
+
+static int winv_offdiag(const Dense& d, const double* A, int64_t lda, int64_t n1, int64_t n2, int64_t base, double* T,
+                        bool t_done, cudaEvent_t t_ready) {
+  double* W = d.Winv + base + base * d.ldw;
+  if (!t_done) {  // T = L21 W11 (W11 lower: k starts at the tile's first column)
+    GemmCall gt{A + n1, W, T, lda, d.ldw, n2, n2, n1, n1, 1.0, 0.0, false, true, false};
+    gt.b_tri = +1;
+    GPC_CHECK(gemm(d, gt));
+  } else if (t_ready) {
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, t_ready, 0));
+  }
+  // W21 = -W22 T (W22 lower: k ends at the tile's last row)
+  GemmCall gw{W + n1 + n1 * d.ldw, T, W + n1, d.ldw, n2, d.ldw, n2, n1, n2, -1.0, 0.0, false, true, false};
+  gw.a_tri = -1;
+  return gemm(d, gw);
+}
+
+int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, double* T, bool defer_top) {
+  double* W = d.Winv + base + base * d.ldw;
+  if (n == TILE)
+    return launch_potrf_leaf(A, lda, d.Dinv + base * TILE, d.info, (int)base, d.nvalid - base, d.logdet, d.s, d.launches,
+                             W, d.ldw);
+  int64_t n1 = split(n), n2 = n - n1;
+  GPC_CHECK(potrf_inv_rec(d, A, lda, n1, base, T, false));
+  double* A21 = A + n1;
+  double* A22 = A + n1 + n1 * lda;
+  {  // L21 = A21 W11'   (W11'(kk, j) = W11(j, kk) is zero for kk > j: k ends at the tile's last column)
+    GemmCall g{A21, W, d.tmpL, lda, d.ldw, n2, n2, n1, n1, 1.0, 0.0, false, false, false};
+    g.b_tri = -1;
+    GPC_CHECK(gemm(d, g));
+    GPC_CHECK(launch_copy_block(d.tmpL, n2, A21, lda, n2, n1, 1.0, d.s, d.launches));
+  }
+  cudaEvent_t t_ready = nullptr;
+  bool t_done = false;
+  if (!defer_top && d.fk) {  // T on a side stream, concurrent with the SYRK and the A22 recursion
+    cudaEvent_t e1 = d.fk->event();
+    t_ready = d.fk->event();
+    Dense ds = d;
+    ds.s = d.fk->stream();
+    GPC_CUDA_CHECK(cudaEventRecord(e1, d.s));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(ds.s, e1, 0));
+    GemmCall gt{A21, W, T, lda, d.ldw, n2, n2, n1, n1, 1.0, 0.0, false, true, false};
+    gt.b_tri = +1;
+    GPC_CHECK(gemm(ds, gt));
+    GPC_CUDA_CHECK(cudaEventRecord(t_ready, ds.s));
+    t_done = true;
+  }
+  {
+    GemmCall g{A21, A21, A22, lda, lda, lda, n2, n2, n1, -1.0, 1.0, false, false, true};
+    GPC_CHECK(gemm(d, g));
+  }
+  GPC_CHECK(potrf_inv_rec(d, A22, lda, n2, base + n1, T + (size_t)n1 * n2, false));
+  if (defer_top) return GPC_OK;
+  return winv_offdiag(d, A, lda, n1, n2, base, T, t_done, t_ready);
+}
+
+int inverse_from_W(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, bool deferred_top) {
+  if (deferred_top && n > TILE) {
+    int64_t n1 = split(n), n2 = n - n1;
+    GPC_CHECK(winv_offdiag(d, L, ldl, n1, n2, 0, d.Tpool, false, nullptr));
+  }
+  // Out(i, j) = sum_{kk >= i} W(kk, i) W(kk, j), i >= j: lower tiles only, k starts at the tile's first row
+  GemmCall g{d.Winv, d.Winv, Out, d.ldw, d.ldw, ldo, n, n, n, 1.0, 0.0, true, true, true};
+  g.a_tri = +1;
+  GPC_CHECK(gemm(d, g));
+  return launch_mirror_lower(Out, ldo, n, d.s, d.launches);
+}
+
 }  // namespace gpc
 
 using namespace gpc;
@@ -200,6 +289,9 @@ struct gpc_ctx {
   int64_t N, Np;
   int D, d;
   double *X, *M, *alpha, *K, *L, *Kinv, *W, *Dinv;
+  double* Winv;    // W = L^-1 (lower block triangle), built by potrf_inv_rec; Kinv doubles as its scratch (tmpL, Tpool)
+  bool w_deferred; // the top-level W21 has not been formed yet
+  bool use_winv;   // GPC_POTRF_MODE != "rec": factor + explicit inverse (default); "rec": recursive TRSM / Schur inverse
   double* scal;    // device scalars: [0] logdet [1] quad [2] trace ; then g[GPC_MAX_PARAMS]
   int* info;       // device
   double* partial; // grad partial sums
@@ -235,14 +327,22 @@ static Dense dense_of(gpc_ctx* c) {
   d.logdet = c->scal + SC_LOGDET;
   d.W = c->W;
   d.nvalid = c->N;
+  d.Winv = c->Winv;
+  d.ldw = c->Np;
+  // scratch inside the (not yet written) K^-1 buffer: tmpL then Tpool
+  d.tmpL = c->Kinv;
+  d.Tpool = c->Kinv ? c->Kinv + (size_t)(c->Npmax / 2 + TILE) * (size_t)(c->Npmax / 2 + TILE) : nullptr;
   return d;
 }
 
 static int ensure_inverse_buffers(gpc_ctx* c) {
   if (c->Kinv) return GPC_OK;
   size_t nn = (size_t)c->Npmax * c->Npmax;
-  GPC_CUDA_CHECK(cudaMalloc(&c->Kinv, nn * sizeof(double)));
-  GPC_CUDA_CHECK(cudaMalloc(&c->W, (potri_workspace(c->Npmax) + 16) * sizeof(double)));
+  // K^-1 also serves as scratch of potrf_inv_rec: tmpL ((Np/2+TILE)^2) + Tpool (<= Np^2/3 + slack)
+  size_t scratch = (size_t)(c->Npmax / 2 + TILE) * (size_t)(c->Npmax / 2 + TILE) + potrf_inv_tspace(c->Npmax) + 16;
+  GPC_CUDA_CHECK(cudaMalloc(&c->Kinv, (nn > scratch ? nn : scratch) * sizeof(double)));
+  if (c->use_winv) GPC_CUDA_CHECK(cudaMalloc(&c->Winv, nn * sizeof(double)));
+  if (!c->use_winv) GPC_CUDA_CHECK(cudaMalloc(&c->W, (potri_workspace(c->Npmax) + 16) * sizeof(double)));
   GPC_CUDA_CHECK(cudaMalloc(&c->symm_part, (size_t)symm_chunks(c->Npmax) * 4 * c->Npmax * sizeof(double)));
   return GPC_OK;
 }
@@ -332,6 +432,10 @@ int gpc_ctx_create(gpc_ctx** out, int device, int64_t Nmax, int Dmax, int dout_m
   c->Dmax = Dmax;
   c->dmax = dout_max;
   c->max_ctas = prop.multiProcessorCount * 2;
+  {
+    const char* mode = getenv("GPC_POTRF_MODE");
+    c->use_winv = !(mode && std::string(mode) == "rec");
+  }
   GPC_CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   size_t np = (size_t)c->Npmax;
@@ -367,7 +471,7 @@ int gpc_ctx_destroy(gpc_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaFree(c->X); cudaFree(c->M); cudaFree(c->alpha); cudaFree(c->K); cudaFree(c->L);
-  cudaFree(c->Kinv); cudaFree(c->W); cudaFree(c->Dinv); cudaFree(c->scal); cudaFree(c->info);
+  cudaFree(c->Kinv); cudaFree(c->Winv); cudaFree(c->W); cudaFree(c->Dinv); cudaFree(c->scal); cudaFree(c->info);
   cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->symm_part); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->tmp1); cudaFree(c->tmp2);
   cudaFreeHost(c->hres); cudaFreeHost(c->hinfo);
   gpc_ctx_set_profile(c, 0);
@@ -494,8 +598,24 @@ static int potrf_async(gpc_ctx* c) {
   GPC_CUDA_CHECK(cudaMemsetAsync(c->info, 0, sizeof(int), c->stream));
   GPC_CUDA_CHECK(cudaMemsetAsync(c->scal + SC_LOGDET, 0, sizeof(double), c->stream));
   GPC_CHECK(launch_copy_lower(c->K, c->Np, c->L, c->Np, c->Np, c->stream, &c->launches));
+  if (c->use_winv) {
+    GPC_CHECK(ensure_inverse_buffers(c));
+    Dense d = dense_of(c);
+    c->w_deferred = true;
+    return potrf_inv_rec(d, c->L, c->Np, c->Np, 0, d.Tpool, true);
+  }
   Dense d = dense_of(c);
   return potrf_rec(d, c->L, c->Np, c->Np, 0);
+}
+
+static int inverse_async(gpc_ctx* c) {
+  Dense d = dense_of(c);
+  if (c->use_winv) {
+    GPC_CHECK(inverse_from_W(d, c->L, c->Np, c->Np, c->Kinv, c->Np, c->w_deferred));
+    c->w_deferred = false;
+    return GPC_OK;
+  }
+  return potri_rec(d, c->L, c->Np, c->Np, c->Kinv, c->Np, 0);
 }
 
 int gpc_potrf(gpc_ctx* c, int* info, double* logdet) {
@@ -565,8 +685,7 @@ int gpc_jitchol(gpc_ctx* c, int max_tries, double* jitter_out, double* logdet) {
 int gpc_inverse(gpc_ctx* c) {
   GPC_CHECK(need(c, c && c->haveL, "gpc_inverse needs a successful gpc_potrf"));
   GPC_CHECK(ensure_inverse_buffers(c));
-  Dense d = dense_of(c);
-  GPC_CHECK(potri_rec(d, c->L, c->Np, c->Np, c->Kinv, c->Np, 0));
+  GPC_CHECK(inverse_async(c));
   c->haveInv = true;
   return GPC_OK;
 }
@@ -786,7 +905,7 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[2], s));
     GPC_CHECK(trace_phase(c, "potrf"));
     // optimistic: queue the rest before looking at info (a failed factorisation is rare and just redone)
-    GPC_CHECK(potri_rec(d, c->L, c->Np, c->Np, c->Kinv, c->Np, 0));
+    GPC_CHECK(inverse_async(c));
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[3], s));
     GPC_CHECK(trace_phase(c, "inverse"));
     GPC_CHECK(alpha_from_inverse_async(c));

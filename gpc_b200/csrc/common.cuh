@@ -53,6 +53,10 @@ struct GemmCall {
   double alpha, beta;
   bool a_kc, b_kc, lower;
   bool ktri = false;  // A operand is zero for kk < i (e.g. rows of L^-T): each row tile starts its k loop at its row
+  // triangular operands (tile-granular k-range skipping; the skipped parts of the operands are never read):
+  //   a_tri = +1: opA(A)(i, kk) == 0 for kk < i (same as ktri);  a_tri = -1: == 0 for kk > i
+  //   b_tri = +1: opB(B)(kk, j) == 0 for kk < j;                  b_tri = -1: == 0 for kk > j
+  int a_tri = 0, b_tri = 0;
 };
 int launch_gemm(const GemmCall& g, cudaStream_t s, int64_t* launches);
 void gemm_force_config(int cfg);  // -1: heuristic (default); 0..4: force a DMMA tile configuration; 100+S: Ozaki, S slices
@@ -70,7 +74,8 @@ void oz_release_device(int dev);   // frees the per-device slice workspace
 // Dinv (TILE x TILE, ld TILE, upper part zero), adds 2*sum(log diag) to *logdet and records the first
 // non-positive pivot (1-based global order = base + j + 1) in *info if *info == 0.
 int launch_potrf_leaf(double* A, int64_t lda, double* Dinv, int* info, int base, int64_t nvalid, double* logdet,
-                      cudaStream_t s, int64_t* launches);
+                      cudaStream_t s, int64_t* launches, double* Wd = nullptr, int64_t ldw = 0);
+                      // Wd != null: the inverse of the factor is also written there with leading dimension ldw
 // misc elementwise / reductions
 int launch_copy_lower(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t n, cudaStream_t s,
                       int64_t* launches);                       // dst lower(+diag) = src lower
@@ -116,7 +121,18 @@ struct Dense {
   double* logdet;  // device
   double* W;       // workspace for the inverse (>= (n/2 + TILE)^2 doubles)
   int64_t nvalid;  // rows below this index are real data (identity padding beyond)
+  // potrf_inv_rec / inverse_from_W (factor + explicit triangular inverse, every solve is one large GEMM):
+  double* Winv = nullptr;  // n_total x n_total, lower block triangle valid: W = L^-1
+  int64_t ldw = 0;
+  double* tmpL = nullptr;  // >= (n/2 + TILE) * (n/2) doubles: out-of-place result of a panel solve
+  double* Tpool = nullptr; // >= tspace(n_total) doubles: T = L21 W11 per recursion depth
 };
+size_t potrf_inv_tspace(int64_t n);  // doubles of Tpool needed for an n x n factorisation
+// in-place lower Cholesky of A (n x n block at row/column `base` of the matrix) AND W = L^-1 of the block into
+// d.Winv; defer_top: the top-level W21 (3/4 of the inverse's flops) is left to inverse_from_W
+int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, double* T, bool defer_top);
+// completes W (if deferred) and forms Out = W' W = (L L')^-1, full symmetric
+int inverse_from_W(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, bool deferred_top);
 int trsm_rlt(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n, int64_t dbase);
 int trsm_rln(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n, int64_t dbase);
 int potrf_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, cudaEvent_t pending = nullptr);

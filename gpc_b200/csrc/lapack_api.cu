@@ -417,7 +417,9 @@ int gpc_gemm_check(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_
   GPC_CUDA_CHECK(cudaMemcpyAsync(dA, A, (size_t)m * k * sizeof(double), cudaMemcpyHostToDevice, sc.s));
   GPC_CUDA_CHECK(cudaMemcpyAsync(dB, B, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice, sc.s));
   GPC_CUDA_CHECK(cudaMemcpyAsync(dC, C, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice, sc.s));
-  GemmCall g{dA, dB, dC, a_kc ? k : m, b_kc ? k : n, m, m, n, k, alpha, beta, a_kc != 0, b_kc != 0, lower != 0};
+  GemmCall g{dA, dB, dC, a_kc ? k : m, b_kc ? k : n, m, m, n, k, alpha, beta, a_kc != 0, b_kc != 0, (lower & 1) != 0};
+  g.a_tri = ((lower >> 1) & 3) == 1 ? 1 : (((lower >> 1) & 3) == 2 ? -1 : 0);
+  g.b_tri = ((lower >> 3) & 3) == 1 ? 1 : (((lower >> 3) & 3) == 2 ? -1 : 0);
   gemm_force_config(cfg);
   int rc = launch_gemm(g, sc.s, &sc.launches);
   gemm_force_config(-1);

@@ -241,7 +241,8 @@ struct OzArgs {
   int kblocks;           // K / 128
   int S, NA;
   int lower;             // skip tiles strictly above the diagonal
-  int ktri;              // A rows are zero for kk < row: start the k loop at the tile's first row
+  int a_tri, b_tri;      // triangular operands: +1 zero for kk < row/col (k loop starts there), -1 zero for kk > row/col
+  int kb_lo, kb_hi;      // k-block range of this launch (k is chunked so that the int32 levels cannot overflow)
   int RpadA, RpadB;      // padded row counts (slice stride in the tensor maps)
   int* errflag;
 };
@@ -314,8 +315,23 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   if (a.lower && bn > 2 * bm + 1) return;  // whole CTA, before any barrier / TMEM allocation
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = bm * OZ_BM, n0 = bn * OZ_BN;
-  const int kb0 = a.ktri ? (m0 / OZ_BK) : 0;
-  const int KB = a.kblocks;
+  int kb0 = a.kb_lo, KB = a.kb_hi;
+  if (a.a_tri > 0 && m0 / OZ_BK > kb0) kb0 = m0 / OZ_BK;
+  if (a.b_tri > 0 && n0 / OZ_BK > kb0) kb0 = n0 / OZ_BK;
+  if (a.a_tri < 0 && (m0 + OZ_BM + OZ_BK - 1) / OZ_BK < KB) KB = (m0 + OZ_BM + OZ_BK - 1) / OZ_BK;
+  if (a.b_tri < 0 && (n0 + OZ_BN + OZ_BK - 1) / OZ_BK < KB) KB = (n0 + OZ_BN + OZ_BK - 1) / OZ_BK;
+  if (kb0 >= KB) {
+    // nothing to accumulate for this tile in this launch: C = beta * C
+    if (a.beta == 1.0) return;
+    if (tid < OZ_BM) {
+      double* crow = a.C + (int64_t)(m0 + tid) + (int64_t)n0 * a.ldc;
+      for (int j = 0; j < OZ_BN; j++) {
+        double* p = crow + (int64_t)j * a.ldc;
+        *p = (a.beta == 0.0) ? 0.0 : a.beta * (*p);
+      }
+    }
+    return;
+  }
 
   // ---- shared memory carve-up (1024-byte aligned for the 128B swizzle atoms)
   const uint32_t raw = smem_u32(oz_smem_raw);
@@ -564,13 +580,17 @@ static double oz_cost_us(const GemmCall& c, int S) {
   const bool same = (c.A == c.B && c.lda == c.ldb && c.a_kc == c.b_kc && c.m == c.n);
   const double elems = (double)c.k * (same ? (double)c.m : (double)(c.m + c.n));
   const double per_k = 0.0267 * (S * (S + 1)) / 72.0;  // us per unit of k per tile wave (S = 8 measured)
-  return 20.0 + elems * (16.0 + S) / 3.0e6 + waves * ((double)c.k * per_k + 5.0);
+  const bool tri = c.ktri || c.a_tri || c.b_tri;
+  const double kfrac = tri ? (c.lower ? 0.67 : 0.5) : 1.0;  // average share of the k range a tile walks
+  return 20.0 + elems * (16.0 + S) / 3.0e6 + waves * ((double)c.k * kfrac * per_k + 5.0);
 }
 static double dmma_cost_us(const GemmCall& c) {
   const double flops = c.lower ? (double)c.m * (double)(c.m + TILE) * (double)c.k : 2.0 * (double)c.m * (double)c.n * (double)c.k;
   const double t64 = c.lower ? (double)(c.m / 64) * (double)(c.m / 64 + 1) / 2.0 : (double)(c.m / 64) * (double)(c.n / 64);
-  const double big = flops / 33.0e6;                                   // 33 TFLOP/s sustained on many-wave problems
-  const double small = ceil(t64 / 296.0) * (double)c.k * 0.0655;      // 64x64 tiles, 2 CTAs per SM
+  const bool tri = c.ktri || c.a_tri || c.b_tri;
+  const double kfrac = tri ? (c.lower ? 0.67 : 0.5) : 1.0;
+  const double big = kfrac * flops / 33.0e6;                                  // 33 TFLOP/s sustained on many-wave problems
+  const double small = ceil(t64 / 296.0) * (double)c.k * kfrac * 0.0655;     // 64x64 tiles, 2 CTAs per SM
   return 4.0 + (big > small ? big : small);
 }
 int oz_slices() {
@@ -583,7 +603,6 @@ bool oz_wants(const GemmCall& c) {
   if (c.C == c.A || c.C == c.B) return false;
   if (c.m % OZ_BM || c.n % OZ_BN || c.k % OZ_BK) return false;
   if (c.m < g_oz_min_mn || c.n < g_oz_min_mn || c.k < g_oz_min_k) return false;
-  if (c.k > 32768) return false;  // int32 level accumulators: (S) * k * 64^2 < 2^31
   if (c.m * (int64_t)OZ_MAXS >= (1LL << 31) || c.n * (int64_t)OZ_MAXS >= (1LL << 31)) return false;
   return oz_cost_us(c, g_oz_S) < g_oz_bias * dmma_cost_us(c);
 }
@@ -664,8 +683,8 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   if (!shared_ws && !w.sl[0]) {
     for (int i = 0; i < 2; i++) GPC_CHECK(ensure_ws(w, i, OZ_SMALL_BYTES, OZ_SMALL_ROWS));
   }
-  if (c.m % OZ_BM || c.n % OZ_BN || c.k % OZ_BK || c.k > 32768 || c.C == c.A || c.C == c.B) {
-    set_error("launch_gemm_ozaki: needs m % 128 == n % 64 == k % 128 == 0, k <= 32768 and C distinct from A, B");
+  if (c.m % OZ_BM || c.n % OZ_BN || c.k % OZ_BK || c.C == c.A || c.C == c.B) {
+    set_error("launch_gemm_ozaki: needs m % 128 == n % 64 == k % 128 == 0 and C distinct from A, B");
     return GPC_ERR_ARG;
   }
   // serialise against the previous Ozaki GEMM (possibly on another stream): the slice buffers are shared
@@ -690,12 +709,19 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   a.S = S;
   a.NA = oz_na(S);
   a.lower = c.lower ? 1 : 0;
-  a.ktri = c.ktri ? 1 : 0;
+  a.a_tri = c.ktri ? 1 : c.a_tri;
+  a.b_tri = c.b_tri;
   a.RpadA = (int)c.m;
   a.RpadB = (int)c.n;
   a.errflag = w.errflag;
   const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
-  switch (S) {
+  // k chunks of <= 256 k-blocks (32768): S products of |digit| <= 64 per level, S * 32768 * 4096 <= 2^30 < 2^31
+  const double beta0 = c.beta;
+  for (int kb = 0; kb < a.kblocks; kb += 256) {
+    a.kb_lo = kb;
+    a.kb_hi = (kb + 256 < a.kblocks) ? kb + 256 : a.kblocks;
+    a.beta = (kb == 0) ? beta0 : 1.0;
+    switch (S) {
 #define OZ_CASE(SS)                                                                                              \
   case SS: {                                                                                                     \
     static bool configured = false;                                                                              \
@@ -706,13 +732,14 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
     }                                                                                                            \
     kern<<<(unsigned)ntiles, OZ_THREADS, oz_smem(SS), s>>>(tmA, tmB, a);                                         \
   } break;
-    OZ_CASE(2) OZ_CASE(3) OZ_CASE(4) OZ_CASE(5) OZ_CASE(6) OZ_CASE(7) OZ_CASE(8)
+      OZ_CASE(2) OZ_CASE(3) OZ_CASE(4) OZ_CASE(5) OZ_CASE(6) OZ_CASE(7) OZ_CASE(8)
 #undef OZ_CASE
-    default:
-      set_error("launch_gemm_ozaki: slices out of range");
-      return GPC_ERR_ARG;
+      default:
+        set_error("launch_gemm_ozaki: slices out of range");
+        return GPC_ERR_ARG;
+    }
+    if (launches) (*launches)++;
   }
-  if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
   GPC_CUDA_CHECK(cudaEventRecord(w.done, s));
   w.used = true;

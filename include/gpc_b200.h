@@ -218,6 +218,9 @@ int gpc_bench_gemm(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_
 int gpc_set_gemm_engine(int ozaki, int slices, int64_t min_mn, int64_t min_k);
 /* One GEMM on HOST arrays in the padded device layouts (m, n multiples of 128, k of 128): A is m x k (ld m) or, with
  * a_kc, k x m (ld k); B likewise n x k / k x n; C m x n (ld m), updated in place: C = alpha op(A) op(B)' + beta C.
+ * lower: bit 0 = only the tiles touching the lower triangle (m == n); bits 1-2 = triangular op(A) (1: zero for kk < i,
+ * 2: zero for kk > i); bits 3-4 = triangular op(B) (1: zero for kk < j, 2: zero for kk > j) -- the zero part of a
+ * triangular operand is skipped tile-wise and never read.
  * cfg: -1 heuristic, 0..4 DMMA tile configuration, 100+S Ozaki with S slices.  Engine parity tests. */
 int gpc_gemm_check(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, double alpha,
                    double beta, const double* A, const double* B, double* C);
