@@ -131,11 +131,17 @@ __device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, int (&r)[16]) {
 // Slicing: fp64 operand (R rows = the m or n index, K deep) -> S int8 slices, K-major [slice][row][k], + row scales
 //   kc = 1: element (r, kk) at g[kk + r*ld];   kc = 0: element (r, kk) at g[r + kk*ld]
 // ------------------------------------------------------------------------------------------------------
+// tri: the operand is triangular in (row, kk) -- +1: zero for kk < row, -1: zero for kk > row.  The zero part is
+// never read (it may be uninitialised memory): rows of 128-row block b only look at kk >= 128 b (+1) / kk < 128 (b+1) (-1),
+// the same 128-granular ranges the GEMM kernel walks.
 __global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict__ g, int64_t ld, int kc, int64_t K,
-                                                       int64_t kchunk, int* __restrict__ emax) {
+                                                       int64_t kchunk, int* __restrict__ emax, int tri) {
   const int tid = threadIdx.x;
-  const int64_t k0 = (int64_t)blockIdx.y * kchunk;
-  const int64_t k1 = (k0 + kchunk < K) ? k0 + kchunk : K;
+  int64_t k0 = (int64_t)blockIdx.y * kchunk;
+  int64_t k1 = (k0 + kchunk < K) ? k0 + kchunk : K;
+  if (tri > 0 && k0 < (int64_t)blockIdx.x * 128) k0 = (int64_t)blockIdx.x * 128;
+  if (tri < 0 && k1 > ((int64_t)blockIdx.x + 1) * 128) k1 = ((int64_t)blockIdx.x + 1) * 128;
+  if (k0 >= k1) return;
   if (!kc) {
     // 128 rows per block; thread pair (h = 0/1) strides over kk
     const int64_t r = (int64_t)blockIdx.x * 128 + (tid & 127);
@@ -173,12 +179,17 @@ constexpr int OZ_SL_STRIDE = OZ_BK + 4;   // 132-byte smem row stride: conflict-
 template <int S>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ g, int64_t ld, int kc, int64_t Rpad,
                                                       int64_t Kpad, const int* __restrict__ emax,
-                                                      int8_t* __restrict__ out, double* __restrict__ scale) {
+                                                      int8_t* __restrict__ out, double* __restrict__ scale, int tri) {
   __shared__ __align__(16) int8_t sm[S * OZ_SL_ROWS * OZ_SL_STRIDE];
   __shared__ double s_inv[OZ_SL_ROWS];
   const int tid = threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.x * OZ_SL_ROWS;
   const int64_t k0 = (int64_t)blockIdx.y * OZ_BK;
+  // k-blocks in the zero part of a triangular operand are neither read nor written (the GEMM never loads them);
+  // the block with blockIdx.y == the row block's own index is always inside the valid range and writes the scales
+  const int64_t rb = r0 / OZ_BM;
+  const bool scale_writer = tri ? ((int64_t)blockIdx.y == rb) : (blockIdx.y == 0);
+  if ((tri > 0 && (int64_t)blockIdx.y < rb) || (tri < 0 && (int64_t)blockIdx.y > rb)) return;
   if (tid < OZ_SL_ROWS) {
     // |x| < 2^(E-1022) for every x of the row (E = largest biased exponent); x' = x * 2^-(E-1022) in (-1, 1)
     int E = emax[r0 + tid];
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
       sc = __longlong_as_double((long long)(Ec + 1) << 52);      // 2^(Ec-1022)
     }
     s_inv[tid] = inv;
-    if (blockIdx.y == 0) scale[r0 + tid] = sc;
+    if (scale_writer) scale[r0 + tid] = sc;
   }
   __syncthreads();
 #pragma unroll 4
@@ -635,13 +646,13 @@ static int ensure_ws(OzWorkspace& w, int which, size_t bytes, size_t rows) {
 
 template <int S>
 static void launch_slice_t(const double* g, int64_t ld, int kc, int64_t R, int64_t K, const int* emax, int8_t* out,
-                           double* scale, cudaStream_t s) {
+                           double* scale, cudaStream_t s, int tri) {
   dim3 grid((unsigned)(R / OZ_SL_ROWS), (unsigned)(K / OZ_BK));
-  oz_slice_kernel<S><<<grid, 256, 0, s>>>(g, ld, kc, R, K, emax, out, scale);
+  oz_slice_kernel<S><<<grid, 256, 0, s>>>(g, ld, kc, R, K, emax, out, scale, tri);
 }
 
 static int slice_operand(OzWorkspace& w, int which, const double* g, int64_t ld, bool kc, int64_t R, int64_t K, int S,
-                         cudaStream_t s, int64_t* launches) {
+                         cudaStream_t s, int64_t* launches, int tri = 0) {
   GPC_CHECK(ensure_ws(w, which, (size_t)S * R * K, (size_t)R));
   GPC_CUDA_CHECK(cudaMemsetAsync(w.emax[which], 0, R * sizeof(int), s));
   // enough blocks to cover the GPU a few times: (R/128) x kchunks >= ~600, chunks of >= 64 columns
@@ -650,16 +661,16 @@ static int slice_operand(OzWorkspace& w, int which, const double* g, int64_t ld,
   if (kchunks < 1) kchunks = 1;
   int64_t kchunk = (K + kchunks - 1) / kchunks;
   dim3 g1((unsigned)(R / 128), (unsigned)kchunks);
-  oz_rowmax_kernel<<<g1, 256, 0, s>>>(g, ld, kc ? 1 : 0, K, kchunk, w.emax[which]);
+  oz_rowmax_kernel<<<g1, 256, 0, s>>>(g, ld, kc ? 1 : 0, K, kchunk, w.emax[which], tri);
   GPC_CUDA_CHECK(cudaGetLastError());
   switch (S) {
-    case 2: launch_slice_t<2>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
-    case 3: launch_slice_t<3>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
-    case 4: launch_slice_t<4>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
-    case 5: launch_slice_t<5>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
-    case 6: launch_slice_t<6>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
-    case 7: launch_slice_t<7>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
-    default: launch_slice_t<8>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s); break;
+    case 2: launch_slice_t<2>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s, tri); break;
+    case 3: launch_slice_t<3>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s, tri); break;
+    case 4: launch_slice_t<4>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s, tri); break;
+    case 5: launch_slice_t<5>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s, tri); break;
+    case 6: launch_slice_t<6>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s, tri); break;
+    case 7: launch_slice_t<7>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s, tri); break;
+    default: launch_slice_t<8>(g, ld, kc, R, K, w.emax[which], w.sl[which], w.scale[which], s, tri); break;
   }
   GPC_CUDA_CHECK(cudaGetLastError());
   if (launches) (*launches) += 2;
@@ -690,8 +701,8 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   // serialise against the previous Ozaki GEMM (possibly on another stream): the slice buffers are shared
   if (w.used) GPC_CUDA_CHECK(cudaStreamWaitEvent(s, w.done, 0));
   const bool same = (c.A == c.B && c.lda == c.ldb && c.a_kc == c.b_kc && c.m == c.n);
-  GPC_CHECK(slice_operand(w, 0, c.A, c.lda, c.a_kc, c.m, c.k, S, s, launches));
-  if (!same) GPC_CHECK(slice_operand(w, 1, c.B, c.ldb, c.b_kc, c.n, c.k, S, s, launches));
+  GPC_CHECK(slice_operand(w, 0, c.A, c.lda, c.a_kc, c.m, c.k, S, s, launches, c.ktri ? 1 : c.a_tri));
+  if (!same) GPC_CHECK(slice_operand(w, 1, c.B, c.ldb, c.b_kc, c.n, c.k, S, s, launches, c.b_tri));
   const int wb = same ? 0 : 1;
   CUtensorMap tmA, tmB;
   GPC_CHECK(make_tmap(&tmA, w.sl[0], (int64_t)S * c.m, c.k, OZ_BM));
