@@ -298,7 +298,8 @@ def main():
         roofline = {
             "bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma.kind::i8 + TMEM + TMA; fp64 via 8 int8 slices) incl. slicing",
             "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
-            "traffic": (traffic or {}).get("oz_gemm_kernel"),
+            "traffic": ((traffic or {}).get("oz_gemm_kernel") or {}).get("dram_bytes_per_launch"),
+            "traffic_note": "ncu --set full, SYRK-shaped call n=8192 k=4096 (profiles/oz_gemm_kernel_ncu_r01.txt); algorithmic bytes of that launch: %s" % ((traffic or {}).get("oz_gemm_kernel") or {}).get("algorithmic_bytes"),
             "peak_source": "fp64-equivalent of the int8 tensor pipe: 2 x %s = %.0f TOP/s, / 36 int8 MMAs per fp64 MMA; "
                            "of measured" % (bf16_src, 2.0 * bf16),
             "launches_per_eval": oz_n, "kernel_ms_per_eval": oz_ms, "algorithmic_flops": oz_fl,
@@ -309,7 +310,7 @@ def main():
         roofline = {
             "bound": "tensor", "kernel": "dgemm_kernel (mma.sync m8n8k4 f64 = DMMA.8x8x4)", "achieved": ach,
             "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value if peak.value else None,
-            "traffic": (traffic or {}).get("dgemm_kernel"),
+            "traffic": ((traffic or {}).get("dgemm_kernel") or {}).get("dram_bytes_per_launch"),
             "peak_source": "measured on this GPU by gpc_bench_dmma_peak (register-resident DMMA loop, burst); "
                            "MEASURED_PEAKS.json has no fp64 figure",
             "launches_per_eval": dm_n, "kernel_ms_per_eval": dm_ms, "algorithmic_flops": dm_fl,
