@@ -267,7 +267,7 @@ def main():
     peak = C.c_double(0)
     check(lib().gpc_bench_dmma_peak(local_rank, C.byref(peak)))
     alg_flops = float(N) ** 3  # potrf N^3/3 + inverse 2N^3/3
-    S = 8
+    S = int(lib().gpc_gemm_engine_slices())
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tfile):
@@ -296,12 +296,13 @@ def main():
         pk = 2.0 * bf16 / (S * (S + 1) / 2.0)
         ach = oz_fl / (oz_ms * 1e-3) / 1e12
         roofline = {
-            "bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma.kind::i8 + TMEM + TMA; fp64 via 8 int8 slices) incl. slicing",
+            "bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma.kind::i8 + TMEM + TMA; fp64 via %d int8 slices) incl. slicing" % S,
             "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
             "traffic": ((traffic or {}).get("oz_gemm_kernel") or {}).get("dram_bytes_per_launch"),
             "traffic_note": "ncu --set full, SYRK-shaped call n=8192 k=4096 (profiles/oz_gemm_kernel_ncu_r01.txt); algorithmic bytes of that launch: %s" % ((traffic or {}).get("oz_gemm_kernel") or {}).get("algorithmic_bytes"),
-            "peak_source": "fp64-equivalent of the int8 tensor pipe: 2 x %s = %.0f TOP/s, / 36 int8 MMAs per fp64 MMA; "
+            "peak_source": "fp64-equivalent of the int8 tensor pipe: 2 x %s = %.0f TOP/s, / S(S+1)/2 int8 MMAs per fp64 MMA; "
                            "of measured" % (bf16_src, 2.0 * bf16),
+            "int8_mmas_per_fp64_mma": S * (S + 1) // 2,
             "launches_per_eval": oz_n, "kernel_ms_per_eval": oz_ms, "algorithmic_flops": oz_fl,
             "share_of_step": oz_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
         }

@@ -402,6 +402,8 @@ int gpc_set_gemm_engine(int ozaki, int slices, int64_t min_mn, int64_t min_k) {
   return GPC_OK;
 }
 
+int gpc_gemm_engine_slices(void) { return oz_slices(); }
+
 int gpc_gemm_check(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, double alpha,
                    double beta, const double* A, const double* B, double* C) {
   if (m % TILE || n % TILE || k % 128 || m < TILE || n < TILE || k < 128 || !A || !B || !C) {

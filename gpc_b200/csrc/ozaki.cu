@@ -5,13 +5,15 @@
 // lapack.h:59-73, CMatrix.cpp:371-432) are therefore computed with the error-free "Ozaki" splitting on the INT8
 // tensor pipe (tcgen05.mma.kind::i8, exact int32 accumulation in TMEM):
 //
-//   a_ik = 2^ea_i * sum_p A_p[i,k] 2^-(7p-1),  A_p int8 in [-64, 64]   (row-wise exponent, balanced base-128 digits)
-//   C_ij = 2^(ea_i+eb_j) * sum_{c=2}^{S+1} 2^-(7c-2) * ( sum_{p+q=c} A_p B_q' )_ij
+//   a_ik = 2^ea_i * sum_p A_p[i,k] 2^-(8p-2),  A_p int8   (row-wise exponent; first digit 6 bits + sign, then balanced
+//                                                         base-256 digits in [-128, 127])
+//   C_ij = 2^(ea_i+eb_j) * sum_{c=2}^{S+1} 2^-(8c-4) * ( sum_{p+q=c} A_p B_q' )_ij
 //
 // Every int8 product is exact; products of equal weight c = p+q share one int32 TMEM accumulator ("level"), so one
-// 128 x 64 output tile owns S levels x 64 columns = all 512 TMEM columns for S = 8.  The S levels are combined in
-// fp64 (Horner, exact power-of-two scalings) by the epilogue warps.  With S = 8 the operands are represented to
-// 55 bits below the row maximum (fp64 has 53), S(S+1)/2 = 36 int8 MMAs replace one fp64 MMA.
+// 128 x 64 output tile owns S levels x 64 TMEM columns = all 512 for S = 8.  The S levels are combined in fp64 (Horner,
+// exact power-of-two scalings) by the epilogue warps.  With S = 8 the operands are represented to 6 + 8*7 = 62 bits
+// below the row maximum (fp64 has 53) and S(S+1)/2 = 36 int8 MMAs replace one fp64 MMA; S = 7 (54 bits, 28 MMAs) matches
+// the fp64 pipe normwise but not for rows with a few dominant entries, where the error is relative to the row maximum.
 //
 // Kernel anatomy (one CTA per output tile, 6 warps):
 //   warp 4 lane 0 : TMA producer -- slices are K-major int8 [slice][row][k]; a k-block (128 B of k) of all S B-slices
@@ -219,14 +221,26 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
       r = (tid >> 7) + 2 * i;
       x = g[(k0 + kk) + (r0 + r) * ld];
     }
+    // first digit: 6 bits + sign (|x'| < 1), every further digit a full balanced byte: x' = d_0 2^-6 + d_1 2^-14 + ...
+    // rint leaves |remainder| <= 1/2, so a raw digit can reach +128: carry it into the next more significant digit
     double v = x * s_inv[r] * 64.0;
     int8_t* dst = sm + r * OZ_SL_STRIDE + kk;
+    int dg[S];
 #pragma unroll
     for (int p = 0; p < S; p++) {
-      double dg = rint(v);
-      dst[p * (OZ_SL_ROWS * OZ_SL_STRIDE)] = (int8_t)(int)dg;
-      v = (v - dg) * 128.0;
+      const double d = rint(v);
+      dg[p] = (int)d;
+      v = (v - d) * 256.0;
     }
+#pragma unroll
+    for (int p = S - 1; p >= 1; p--) {
+      if (dg[p] > 127) {
+        dg[p] -= 256;
+        dg[p - 1] += 1;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < S; p++) dst[p * (OZ_SL_ROWS * OZ_SL_STRIDE)] = (int8_t)dg[p];
   }
   __syncthreads();
   // write out: S * 32 rows of 128 contiguous bytes, 16 B per thread
@@ -472,7 +486,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       for (int l = S - 2; l >= 0; l--) {
         oz_tmem_ld16(trow + (uint32_t)(l * OZ_BN + ch * 16), r);
 #pragma unroll
-        for (int j = 0; j < 16; j++) acc[j] = fma(acc[j], 0.0078125, (double)r[j]);
+        for (int j = 0; j < 16; j++) acc[j] = fma(acc[j], 0.00390625, (double)r[j]);  // 2^-8 per level
       }
 #pragma unroll
       for (int j = 0; j < 16; j++) {
@@ -590,7 +604,7 @@ static double oz_cost_us(const GemmCall& c, int S) {
   const double waves = ceil(tiles / 148.0);
   const bool same = (c.A == c.B && c.lda == c.ldb && c.a_kc == c.b_kc && c.m == c.n);
   const double elems = (double)c.k * (same ? (double)c.m : (double)(c.m + c.n));
-  const double per_k = 0.0267 * (S * (S + 1)) / 72.0;  // us per unit of k per tile wave (S = 8 measured)
+  const double per_k = 0.0267 * (S * (S + 1)) / 72.0;  // us per unit of k per tile wave (36 products measured)
   const bool tri = c.ktri || c.a_tri || c.b_tri;
   const double kfrac = tri ? (c.lower ? 0.67 : 0.5) : 1.0;  // average share of the k range a tile walks
   return 20.0 + elems * (16.0 + S) / 3.0e6 + waves * ((double)c.k * kfrac * per_k + 5.0);
@@ -726,11 +740,13 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   a.RpadB = (int)c.n;
   a.errflag = w.errflag;
   const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
-  // k chunks of <= 256 k-blocks (32768): S products of |digit| <= 64 per level, S * 32768 * 4096 <= 2^30 < 2^31
+  // k chunks: per unit of k a level sums <= 8 products, two of them with a first digit (|d_0| <= 65), the others with
+  // |d| <= 128: (6 * 2^14 + 2 * 65 * 128) * k < 2^31  ->  k <= 18683: chunks of 128 k-blocks (16384)
+  const int kchunk = 128;
   const double beta0 = c.beta;
-  for (int kb = 0; kb < a.kblocks; kb += 256) {
+  for (int kb = 0; kb < a.kblocks; kb += kchunk) {
     a.kb_lo = kb;
-    a.kb_hi = (kb + 256 < a.kblocks) ? kb + 256 : a.kblocks;
+    a.kb_hi = (kb + kchunk < a.kblocks) ? kb + kchunk : a.kblocks;
     a.beta = (kb == 0) ? beta0 : 1.0;
     switch (S) {
 #define OZ_CASE(SS)                                                                                              \

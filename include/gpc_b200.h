@@ -211,11 +211,14 @@ int gpc_bench_gemm(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_
 /* The dsyrk_/dgemm_ work below dpotrf_/dpotri_ (lapack.h:59-73) runs on one of two engines:
  *   DMMA  : mma.sync.m8n8k4.f64 (the fp64 tensor pipe, 37 TFLOP/s peak);
  *   OZAKI : error-free splitting into `slices` int8 planes multiplied exactly on tcgen05.mma.kind::i8 with int32
- *           accumulators in TMEM and recombined in fp64 (6 + 7(slices-1) bits below each row's largest entry; 8 slices
- *           = 55 bits).  Used for calls with m, n >= min_mn and k >= min_k.
+ *           accumulators in TMEM and recombined in fp64 (6 + 8(slices-1) bits below each row's largest entry; the
+ *           default 8 slices = 62 bits, fp64 has 53).  Used for calls with m, n >= min_mn and k >= min_k that the
+ *           engine cost model expects to be faster.
  * ozaki: 0 = DMMA only, 1 = Ozaki for large calls, -1 = leave; slices 2..8 (0 = leave); min_* <= 0 = leave.
  * Process-wide; initial values come from GPC_OZAKI, GPC_OZAKI_SLICES, GPC_OZAKI_MIN_MN, GPC_OZAKI_MIN_K. */
 int gpc_set_gemm_engine(int ozaki, int slices, int64_t min_mn, int64_t min_k);
+/* the number of slices currently configured */
+int gpc_gemm_engine_slices(void);
 /* One GEMM on HOST arrays in the padded device layouts (m, n multiples of 128, k of 128): A is m x k (ld m) or, with
  * a_kc, k x m (ld k); B likewise n x k / k x n; C m x n (ld m), updated in place: C = alpha op(A) op(B)' + beta C.
  * lower: bit 0 = only the tiles touching the lower triangle (m == n); bits 1-2 = triangular op(A) (1: zero for kk < i,
@@ -227,7 +230,7 @@ int gpc_gemm_check(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_
 
 /* The Ozaki splitting of one HOST operand (R rows = the m or n index, K deep; kc: k contiguous, ld K, else ld R):
  * slices_out receives S planes of R x K int8 (k contiguous), scale_out the R row scales 2^e_r, such that
- * x[r,k] = scale[r] * sum_p slices[p][r][k] * 2^-(7p+6) (p = 0..S-1) to 6+7(S-1) bits.  Test hook of the slicing kernel. */
+ * x[r,k] = scale[r] * sum_p slices[p][r][k] * 2^-(8p+6) (p = 0..S-1) to 6+8(S-1) bits.  Test hook of the slicing kernel. */
 int gpc_oz_slice_check(int device, int64_t R, int64_t K, int kc, int S, const double* X, signed char* slices_out,
                        double* scale_out);
 

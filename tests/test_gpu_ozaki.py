@@ -24,15 +24,15 @@ def _slices(R, K, kc, S, rng):
 
 
 @pytest.mark.parametrize("kc", [0, 1])
-@pytest.mark.parametrize("S", [8, 6, 3])
+@pytest.mark.parametrize("S", [8, 7, 3])
 def test_slicing_is_exact_to_the_last_digit(kc, S):
-    """x = 2^e_r * sum_p d_p 2^-(7p+6) with |d_p| <= 64 and a remainder below half a unit of the last digit."""
+    """x = 2^e_r * sum_p d_p 2^-(8p+6), d_0 in [-65, 65], d_p a balanced byte, remainder below half a unit of the last digit."""
     rng = np.random.default_rng(11 + S)
     X, sl, sc = _slices(256, 384, kc, S, rng)
-    assert np.abs(sl.astype(int)).max() <= 64
+    assert np.abs(sl[0].astype(int)).max() <= 65
     rec = np.zeros(X.shape, dtype=np.longdouble)
     for p in range(S):
-        rec += sl[p].astype(np.longdouble) * np.longdouble(2.0) ** (-(7 * p + 6))
+        rec += sl[p].astype(np.longdouble) * np.longdouble(2.0) ** (-(8 * p + 6))
     rec *= sc[:, None].astype(np.longdouble)
     # scales are powers of two strictly above the row maximum (or the smallest normal scale for a zero row)
     m, e = np.frexp(sc)
@@ -40,7 +40,7 @@ def test_slicing_is_exact_to_the_last_digit(kc, S):
     rowmax = np.max(np.abs(X), axis=1)
     assert np.all(sc[rowmax > 0] > rowmax[rowmax > 0]) and np.all(sc[rowmax > 0] <= 2 * rowmax[rowmax > 0])
     err = np.abs(rec - X.astype(np.longdouble))
-    bound = sc[:, None] * 2.0 ** -(6 + 7 * (S - 1) + 1)
+    bound = sc[:, None] * 2.0 ** -(6 + 8 * (S - 1) + 1)
     assert np.all(err <= bound * (1 + 1e-12))
     assert np.all(sl[:, 3, :] == 0)
 
@@ -87,9 +87,9 @@ def _gemm(m, n, k, a_kc, b_kc, flags, cfg, alpha, beta, rng, wide=False, rowmax_
 def test_ozaki_gemm_matches_fp64_all_layouts(a_kc, b_kc):
     rng = np.random.default_rng(100 + 2 * a_kc + b_kc)
     e = _gemm(256, 384, 512, a_kc, b_kc, 0, 108, -1.0, 1.0, rng)
-    assert e < 4e-16, e
+    assert e < 1.5e-16, e   # the final rounding of the fp64 result dominates
     e = _gemm(256, 256, 256, a_kc, b_kc, 0, 108, 0.5, 0.0, rng, wide=True)
-    assert e < 4e-16, e
+    assert e < 1.5e-16, e
 
 
 def test_ozaki_is_at_least_as_accurate_as_dmma():
@@ -97,7 +97,7 @@ def test_ozaki_is_at_least_as_accurate_as_dmma():
     e_oz = _gemm(512, 512, 2048, 0, 0, 0, 108, -1.0, 1.0, rng)
     rng = np.random.default_rng(5)
     e_dm = _gemm(512, 512, 2048, 0, 0, 0, 0, -1.0, 1.0, rng)
-    assert e_oz < 4e-16 and e_oz <= 2 * e_dm, (e_oz, e_dm)
+    assert e_oz < 1e-16 and e_oz <= e_dm, (e_oz, e_dm)
 
 
 @pytest.mark.parametrize("cfg", [108, -1])
@@ -111,7 +111,7 @@ def test_lower_and_triangular_k_ranges(flags, cfg):
     assert e < (1e-15 if cfg >= 100 else 1e-14), (flags, cfg, e)  # the DMMA engine accumulates k = 512 products in fp64
 
 
-@pytest.mark.parametrize("S,tol", [(7, 5e-14), (6, 5e-12), (4, 1e-7)])
+@pytest.mark.parametrize("S,tol", [(7, 2e-15), (6, 5e-13), (5, 1e-10), (3, 5e-6)])
 def test_fewer_slices_degrade_as_documented(S, tol):
     rng = np.random.default_rng(3)
     e = _gemm(256, 256, 1024, 0, 0, 0, 100 + S, -1.0, 1.0, rng)

@@ -22,11 +22,11 @@ def slice_check(R, K, kc, S):
     check(L.gpc_oz_slice_check(0, R, K, kc, S, ptr(Xd), ptr(sl), ptr(sc)))
     rec = np.zeros((R, K), dtype=np.longdouble)
     for p in range(S):
-        rec += sl[p].astype(np.longdouble) * np.longdouble(2.0) ** (-(7 * p + 6))
+        rec += sl[p].astype(np.longdouble) * np.longdouble(2.0) ** (-(8 * p + 6))
     rec *= sc[:, None].astype(np.longdouble)
     err = np.max(np.abs(rec - X.astype(np.longdouble)) / np.max(np.abs(X), axis=1, keepdims=True))
     print("slice R=%d K=%d kc=%d S=%d: max |digit|=%d, rel-to-rowmax err=%.3e (bound %.3e)" % (
-        R, K, kc, S, np.abs(sl.astype(int)).max(), float(err), 2.0 ** -(6 + 7 * (S - 1) + 1)), flush=True)
+        R, K, kc, S, np.abs(sl.astype(int)).max(), float(err), 2.0 ** -(6 + 8 * (S - 1) + 1)), flush=True)
 
 
 def gemm_case(m, n, k, a_kc, b_kc, lower, cfg, alpha=-1.0, beta=1.0, wide=False):
@@ -70,7 +70,7 @@ if __name__ == "__main__":
         gemm_case(256, 256, 512, 0, 1, 0, 108, alpha=1.0, beta=0.0)
         gemm_case(256, 256, 512, 1, 0, 0, 108, wide=True)
         gemm_case(512, 512, 512, 0, 0, 1, 108)
-        for S in (7, 6, 4):
+        for S in (7, 6, 5, 4, 3):
             gemm_case(256, 256, 1024, 0, 0, 0, 100 + S)
         gemm_case(1024, 1024, 4096, 0, 0, 0, 108)
         gemm_case(1024, 1024, 4096, 0, 0, 0, 0)
