@@ -65,7 +65,9 @@ int trsm_rlt(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L,
                     int64_t dbase) {
   if (m <= 0) return GPC_OK;
   if (n == TILE) {
-    GemmCall g{B, d.Dinv + dbase * TILE, B, ldb, TILE, ldb, m, TILE, TILE, 1.0, 0.0, false, false, false};
+    int64_t ldd;
+    const double* Di = d.dinv_blk(dbase, &ldd);
+    GemmCall g{B, Di, B, ldb, ldd, ldb, m, TILE, TILE, 1.0, 0.0, false, false, false};
     return gemm(d, g);  // force-128 rule inside launch_gemm keeps in-place safe (n == TILE)
   }
   int64_t n1 = split(n), n2 = n - n1;
@@ -80,7 +82,9 @@ int trsm_rln(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L,
                     int64_t dbase) {
   if (m <= 0) return GPC_OK;
   if (n == TILE) {
-    GemmCall g{B, d.Dinv + dbase * TILE, B, ldb, TILE, ldb, m, TILE, TILE, 1.0, 0.0, false, true, false};
+    int64_t ldd;
+    const double* Di = d.dinv_blk(dbase, &ldd);
+    GemmCall g{B, Di, B, ldb, ldd, ldb, m, TILE, TILE, 1.0, 0.0, false, true, false};
     return gemm(d, g);
   }
   int64_t n1 = split(n), n2 = n - n1;
@@ -226,8 +230,7 @@ static int winv_offdiag(const Dense& d, const double* A, int64_t lda, int64_t n1
 int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, double* T, bool defer_top) {
   double* W = d.Winv + base + base * d.ldw;
   if (n == TILE)
-    return launch_potrf_leaf(A, lda, d.Dinv + base * TILE, d.info, (int)base, d.nvalid - base, d.logdet, d.s, d.launches,
-                             W, d.ldw);
+    return launch_potrf_leaf(A, lda, nullptr, d.info, (int)base, d.nvalid - base, d.logdet, d.s, d.launches, W, d.ldw);
   int64_t n1 = split(n), n2 = n - n1;
   GPC_CHECK(potrf_inv_rec(d, A, lda, n1, base, T, false));
   double* A21 = A + n1;
@@ -291,6 +294,7 @@ struct gpc_ctx {
   double *X, *M, *alpha, *K, *L, *Kinv, *W, *Dinv;
   double* Winv;    // W = L^-1 (lower block triangle), built by potrf_inv_rec; Kinv doubles as its scratch (tmpL, Tpool)
   bool w_deferred; // the top-level W21 has not been formed yet
+  int64_t winv_np; // padded size for which the diagonal blocks of Winv have zero strict upper parts (0: never)
   bool use_winv;   // GPC_POTRF_MODE != "rec": factor + explicit inverse (default); "rec": recursive TRSM / Schur inverse
   double* scal;    // device scalars: [0] logdet [1] quad [2] trace ; then g[GPC_MAX_PARAMS]
   int* info;       // device
@@ -600,6 +604,11 @@ static int potrf_async(gpc_ctx* c) {
   GPC_CHECK(launch_copy_lower(c->K, c->Np, c->L, c->Np, c->Np, c->stream, &c->launches));
   if (c->use_winv) {
     GPC_CHECK(ensure_inverse_buffers(c));
+    if (c->winv_np != c->Np) {
+      // the leaf writes only the lower part of W's diagonal blocks: zero the strict upper parts once per layout
+      GPC_CUDA_CHECK(cudaMemsetAsync(c->Winv, 0, (size_t)c->Np * c->Np * sizeof(double), c->stream));
+      c->winv_np = c->Np;
+    }
     Dense d = dense_of(c);
     c->w_deferred = true;
     return potrf_inv_rec(d, c->L, c->Np, c->Np, 0, d.Tpool, true);

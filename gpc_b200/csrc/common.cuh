@@ -76,6 +76,7 @@ void oz_release_device(int dev);   // frees the per-device slice workspace
 int launch_potrf_leaf(double* A, int64_t lda, double* Dinv, int* info, int base, int64_t nvalid, double* logdet,
                       cudaStream_t s, int64_t* launches, double* Wd = nullptr, int64_t ldw = 0);
                       // Wd != null: the inverse of the factor is also written there with leading dimension ldw
+void leaf_set_debug(long long* dev_stamps);  // phase time stamps of the next leaf launches (null: off)
 // misc elementwise / reductions
 int launch_copy_lower(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t n, cudaStream_t s,
                       int64_t* launches);                       // dst lower(+diag) = src lower
@@ -126,6 +127,15 @@ struct Dense {
   int64_t ldw = 0;
   double* tmpL = nullptr;  // >= (n/2 + TILE) * (n/2) doubles: out-of-place result of a panel solve
   double* Tpool = nullptr; // >= tspace(n_total) doubles: T = L21 W11 per recursion depth
+  // inverse of the diagonal block of the factor at row/column dbase: the diagonal block of W when W is kept, else Dinv
+  const double* dinv_blk(int64_t dbase, int64_t* ld) const {
+    if (Winv) {
+      *ld = ldw;
+      return Winv + dbase + dbase * ldw;
+    }
+    *ld = TILE;
+    return Dinv + dbase * TILE;
+  }
 };
 size_t potrf_inv_tspace(int64_t n);  // doubles of Tpool needed for an n x n factorisation
 // in-place lower Cholesky of A (n x n block at row/column `base` of the matrix) AND W = L^-1 of the block into

@@ -404,6 +404,54 @@ int gpc_set_gemm_engine(int ozaki, int slices, int64_t min_mn, int64_t min_k) {
 
 int gpc_gemm_engine_slices(void) { return oz_slices(); }
 
+int gpc_bench_leaf(int device, int reps, double* us_out, long long* stamps_out) {
+  // the 128 x 128 diagonal-block kernel on a well-conditioned SPD block, timed in isolation; stamps_out (32 entries)
+  // receives the clock64 phase stamps of the last launch relative to its start
+  if (reps < 1) return GPC_ERR_ARG;
+  Scratch sc;
+  GPC_CHECK(sc.init(device));
+  double *A, *A0, *Dinv, *W, *ld;
+  int* info;
+  long long* st;
+  GPC_CHECK(sc.alloc(&A, (size_t)TILE * TILE, true));
+  GPC_CHECK(sc.alloc(&A0, (size_t)TILE * TILE, true));
+  GPC_CHECK(sc.alloc(&Dinv, (size_t)TILE * TILE, true));
+  GPC_CHECK(sc.alloc(&W, (size_t)TILE * TILE, true));
+  GPC_CHECK(sc.alloc(&ld, 8, true));
+  GPC_CHECK(sc.alloc((double**)&info, 8, true));
+  GPC_CHECK(sc.alloc((double**)&st, 64, true));
+  std::vector<double> h((size_t)TILE * TILE);
+  for (int j = 0; j < TILE; j++)
+    for (int i = 0; i < TILE; i++) h[i + (size_t)j * TILE] = (i == j ? 2.0 : 0.0) + exp(-0.05 * (i - j) * (i - j));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(A0, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, sc.s));
+  cudaEvent_t e0, e1;
+  GPC_CUDA_CHECK(cudaEventCreate(&e0));
+  GPC_CUDA_CHECK(cudaEventCreate(&e1));
+  float total = 0.f;
+  for (int r = 0; r < reps + 1; r++) {
+    GPC_CUDA_CHECK(cudaMemcpyAsync(A, A0, h.size() * sizeof(double), cudaMemcpyDeviceToDevice, sc.s));
+    if (r == reps) leaf_set_debug(st);
+    GPC_CUDA_CHECK(cudaEventRecord(e0, sc.s));
+    int rc = launch_potrf_leaf(A, TILE, nullptr, info, 0, TILE, ld, sc.s, &sc.launches, W, TILE);
+    leaf_set_debug(nullptr);
+    if (rc != GPC_OK) return rc;
+    GPC_CUDA_CHECK(cudaEventRecord(e1, sc.s));
+    GPC_CUDA_CHECK(cudaStreamSynchronize(sc.s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && r < reps) total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (us_out) *us_out = 1e3 * total / (reps > 1 ? reps - 1 : 1);
+  if (stamps_out) {
+    long long hs[32];
+    GPC_CUDA_CHECK(cudaMemcpy(hs, st, sizeof(hs), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 32; i++) stamps_out[i] = hs[i] ? hs[i] - hs[0] : 0;
+  }
+  return GPC_OK;
+}
+
 int gpc_gemm_check(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, double alpha,
                    double beta, const double* A, const double* B, double* C) {
   if (m % TILE || n % TILE || k % 128 || m < TILE || n < TILE || k < 128 || !A || !B || !C) {

@@ -203,6 +203,9 @@ int gpc_dev_grad_cols(gpc_dev* h, const gpc_kcomp* comps, int ncomp, const doubl
 int gpc_bench_dmma_peak(int device, double* tflops);
 /* C(n x n) -= A(n x k) A' (lower) on device scratch: the SYRK trailing update in isolation.  *ms per launch */
 int gpc_bench_syrk(int device, int64_t n, int64_t k, int reps, double* ms);
+/* the 128 x 128 diagonal-block kernel (Cholesky + inverse of the factor, N/128 times on the critical path) in
+ * isolation: *us per launch; stamps (32 entries) = clock64 phase stamps of one launch relative to its start */
+int gpc_bench_leaf(int device, int reps, double* us, long long* stamps);
 /* one GEMM shape on device scratch with a forced tile configuration (cfg 0..3, -1 = heuristic): kernel tuning */
 int gpc_bench_gemm(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, int reps,
                    double* ms);
