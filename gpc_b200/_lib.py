@@ -37,7 +37,7 @@ SYMBOLS = [
     "gpc_ctx_get_stream", "gpc_ctx_sync", "gpc_ctx_launch_count", "gpc_set_X", "gpc_set_M", "gpc_set_Y",
     "gpc_kern_build", "gpc_kern_cross", "gpc_kern_diag", "gpc_add_diag", "gpc_potrf", "gpc_jitchol",
     "gpc_solve_alpha", "gpc_inverse", "gpc_alpha_from_inverse", "gpc_grad", "gpc_kern_grad", "gpc_posterior",
-    "gpc_eval", "gpc_download", "gpc_last_timings", "gpc_dpotrf", "gpc_dpotri", "gpc_dtrsm", "gpc_dsyrk",
+    "gpc_eval", "gpc_download", "gpc_last_timings", "gpc_last_enqueue_ms", "gpc_dpotrf", "gpc_dpotri", "gpc_dtrsm", "gpc_dsyrk",
     "gpc_dgemm", "gpc_dsymv", "gpc_bench_dmma_peak", "gpc_bench_syrk", "gpc_ctx_set_profile", "gpc_last_gemm_profile", "gpc_last_gemm_profile_split", "gpc_bench_gemm", "gpc_dev_create", "gpc_dev_destroy", "gpc_dev_set_stream",
     "gpc_bench_leaf", "gpc_set_gemm_engine", "gpc_gemm_engine_slices", "gpc_gemm_check", "gpc_oz_slice_check",
     "gpc_dev_launch_count", "gpc_dev_potrf", "gpc_dev_trsm", "gpc_dev_gemm", "gpc_dev_kbuild_cols", "gpc_dev_grad_cols",
@@ -85,6 +85,7 @@ def lib():
     L.gpc_eval.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gpc_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, i64]
     L.gpc_last_timings.argtypes = [C.c_void_p, C.c_void_p]
+    L.gpc_last_enqueue_ms.argtypes = [C.c_void_p, c_double_p]
     L.gpc_dpotrf.argtypes = [C.c_int, C.c_char, i64, C.c_void_p, i64, c_int_p]
     L.gpc_dpotri.argtypes = [C.c_int, C.c_char, i64, C.c_void_p, i64, c_int_p]
     L.gpc_dtrsm.argtypes = [C.c_int, C.c_char, C.c_char, C.c_char, C.c_char, i64, i64, C.c_double, C.c_void_p, i64,

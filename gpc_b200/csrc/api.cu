@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <chrono>
 #include "common.cuh"
 
 namespace gpc {
@@ -309,12 +310,13 @@ struct gpc_ctx {
   cudaEvent_t ev[6];
   double last_ms[6];
   // scratch for cross-covariances (grown on demand)
-  double *Xs, *Kc, *tmp1, *tmp2;
+  double *Xs, *Kc, *Kc2, *tmp1, *tmp2;
   int64_t Xs_cap, Kc_cap, tmp_cap;
   Fork* fork;           // side streams / events for the recursions
   GemmProf* prof;       // non-null in profiling mode
   double prof_ms, prof_flops;
   int64_t prof_count;
+  double enqueue_ms;     // host time gpc_eval spent queueing the last evaluation (before its single synchronisation)
   double prof_split[8];  // DMMA [ms, flops, launches, 0], Ozaki [ms, fp64-equivalent flops, launches, int8 ops]
 };
 
@@ -476,7 +478,7 @@ int gpc_ctx_destroy(gpc_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->X); cudaFree(c->M); cudaFree(c->alpha); cudaFree(c->K); cudaFree(c->L);
   cudaFree(c->Kinv); cudaFree(c->Winv); cudaFree(c->W); cudaFree(c->Dinv); cudaFree(c->scal); cudaFree(c->info);
-  cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->symm_part); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->tmp1); cudaFree(c->tmp2);
+  cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->symm_part); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->Kc2); cudaFree(c->tmp1); cudaFree(c->tmp2);
   cudaFreeHost(c->hres); cudaFreeHost(c->hinfo);
   gpc_ctx_set_profile(c, 0);
   if (c->fork) {
@@ -793,6 +795,31 @@ int gpc_kern_grad(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* c
   return GPC_OK;
 }
 
+// V = B L^-T (the right-sided solve V L' = B) through W = L^-1, out of place: one triangular product when W is
+// complete; while the top-level W21 is still deferred the top level is done by block substitution instead
+// (V1 = B1 W11', B2 -= V1 L21', V2 = B2 W22'), which needs only the diagonal halves of W.  B is overwritten.
+static int solve_rlt_via_W(gpc_ctx* c, const Dense& d, double* B, int64_t ldb, int64_t m, double* V, int64_t ldv) {
+  const int64_t n = c->Np;
+  if (!c->w_deferred || n <= TILE) {
+    GemmCall g{B, d.Winv, V, ldb, d.ldw, ldv, m, n, n, 1.0, 0.0, false, false, false};
+    g.b_tri = -1;
+    return launch_gemm(g, d.s, d.launches);
+  }
+  const int64_t n1 = (n / TILE / 2) * TILE, n2 = n - n1;
+  {
+    GemmCall g{B, d.Winv, V, ldb, d.ldw, ldv, m, n1, n1, 1.0, 0.0, false, false, false};
+    g.b_tri = -1;
+    GPC_CHECK(launch_gemm(g, d.s, d.launches));
+  }
+  {  // B2 -= V1 L21'
+    GemmCall g{V, c->L + n1, B + n1 * ldb, ldv, c->Np, ldb, m, n2, n1, -1.0, 1.0, false, false, false};
+    GPC_CHECK(launch_gemm(g, d.s, d.launches));
+  }
+  GemmCall g{B + n1 * ldb, d.Winv + n1 + n1 * d.ldw, V + n1 * ldv, ldb, d.ldw, ldv, m, n2, n2, 1.0, 0.0, false, false, false};
+  g.b_tri = -1;
+  return launch_gemm(g, d.s, d.launches);
+}
+
 static int ensure_cross(gpc_ctx* c, int64_t Nsp) {
   if (c->Xs_cap < Nsp * c->Dmax) {
     cudaFree(c->Xs);
@@ -802,8 +829,10 @@ static int ensure_cross(gpc_ctx* c, int64_t Nsp) {
   }
   if (c->Kc_cap < Nsp * c->Np) {
     cudaFree(c->Kc);
-    c->Kc = nullptr;
+    cudaFree(c->Kc2);
+    c->Kc = c->Kc2 = nullptr;
     GPC_CUDA_CHECK(cudaMalloc(&c->Kc, (size_t)Nsp * c->Np * sizeof(double)));
+    if (c->use_winv) GPC_CUDA_CHECK(cudaMalloc(&c->Kc2, (size_t)Nsp * c->Np * sizeof(double)));
     c->Kc_cap = Nsp * c->Np;
   }
   return GPC_OK;
@@ -863,9 +892,15 @@ int gpc_posterior(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* X
   if (var) {
     // var = k(x*,x*) - |L^-1 k*|^2  (CGp::_posteriorVar FTC, CGp.cpp:600-613)
     Dense d = dense_of(c);
-    GPC_CHECK(trsm_rlt(d, c->Kc, Nsp, Nsp, c->L, c->Np, c->Np, 0));
+    const double* Vm = c->Kc;
+    if (c->use_winv && c->Kc2) {  // V = Kc L^-T as products with W = L^-1 (large GEMMs on the tensor-core engine)
+      GPC_CHECK(solve_rlt_via_W(c, d, c->Kc, Nsp, Nsp, c->Kc2, Nsp));
+      Vm = c->Kc2;
+    } else {
+      GPC_CHECK(trsm_rlt(d, c->Kc, Nsp, Nsp, c->L, c->Np, c->Np, 0));
+    }
     GPC_CHECK(launch_kdiag(ks, c->Xs, Nsp, Ns, c->tmp2, c->stream, &c->launches));
-    GPC_CHECK(launch_row_sqnorm_sub(c->Kc, Nsp, Ns, c->N, c->tmp2, c->tmp1, c->stream, &c->launches));
+    GPC_CHECK(launch_row_sqnorm_sub(Vm, Nsp, Ns, c->N, c->tmp2, c->tmp1, c->stream, &c->launches));
     std::vector<double> v((size_t)Ns);
     GPC_CHECK(download(c, v.data(), Ns, c->tmp1, Nsp, Ns, 1));
     for (int j = 0; j < c->d; j++)  // same variance for every output (CGp.cpp:608-611)
@@ -896,6 +931,7 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
   bool wantX = (flags & 1) && gX;
   Dense d = dense_of(c);
   cudaStream_t s = c->stream;
+  const auto host_t0 = std::chrono::steady_clock::now();
   GPC_CUDA_CHECK(cudaEventRecord(c->ev[0], s));
   GPC_CHECK(launch_kbuild(ks, c->X, c->Np, c->N, c->Np, c->K, c->Np, s, &c->launches));
   c->haveK = true;
@@ -925,6 +961,7 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
     GPC_CHECK(trace_phase(c, "grad"));
     GPC_CUDA_CHECK(cudaMemcpyAsync(c->hinfo, c->info, sizeof(int), cudaMemcpyDeviceToHost, s));
     GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres, c->scal, (SC_G + ks.nparams) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    c->enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     GPC_CUDA_CHECK(cudaStreamSynchronize(s));
     if (*c->hinfo == 0) break;
     // jitChol schedule (CMatrix.cpp:767-804)
@@ -1017,6 +1054,11 @@ int gpc_last_gemm_profile_split(gpc_ctx* c, double* out8) {
 int gpc_last_timings(gpc_ctx* c, double* ms6) {
   if (!c || !ms6) return GPC_ERR_ARG;
   for (int i = 0; i < 6; i++) ms6[i] = c->last_ms[i];
+  return GPC_OK;
+}
+int gpc_last_enqueue_ms(gpc_ctx* c, double* ms) {
+  if (!c || !ms) return GPC_ERR_ARG;
+  *ms = c->enqueue_ms;
   return GPC_OK;
 }
 

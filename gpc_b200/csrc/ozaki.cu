@@ -705,8 +705,9 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   const size_t op_bytes = (size_t)S * (size_t)(c.m > c.n ? c.m : c.n) * (size_t)c.k;
   const bool shared_ws = op_bytes > OZ_SMALL_BYTES;
   OzWorkspace& w = shared_ws ? g_oz_ws[dev] : g_oz_pool[dev][g_oz_pool_next[dev]++ % OZ_POOL];
-  if (!shared_ws && !w.sl[0]) {
-    for (int i = 0; i < 2; i++) GPC_CHECK(ensure_ws(w, i, OZ_SMALL_BYTES, OZ_SMALL_ROWS));
+  if (!shared_ws && !w.sl[0]) {  // first small call on this device: allocate the whole pool now, not over 8 calls
+    for (int q = 0; q < OZ_POOL; q++)
+      for (int i = 0; i < 2; i++) GPC_CHECK(ensure_ws(g_oz_pool[dev][q], i, OZ_SMALL_BYTES, OZ_SMALL_ROWS));
   }
   if (c.m % OZ_BM || c.n % OZ_BN || c.k % OZ_BK || c.C == c.A || c.C == c.B) {
     set_error("launch_gemm_ozaki: needs m % 128 == n % 64 == k % 128 == 0 and C distinct from A, B");

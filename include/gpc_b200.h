@@ -142,6 +142,8 @@ int gpc_download(gpc_ctx* ctx, int which, double* dst, int64_t ld);
 /* phase timings of the last gpc_eval in milliseconds (CUDA events on the context's stream):
  * [0] K build [1] potrf [2] inverse [3] alpha+reductions [4] gradient [5] total */
 int gpc_last_timings(gpc_ctx* ctx, double* ms6);
+/* host milliseconds the last gpc_eval spent queueing work before its single synchronisation (launch-bound check) */
+int gpc_last_enqueue_ms(gpc_ctx* ctx, double* ms);
 
 /* profiling mode (bench.py roofline): bracket every DMMA GEMM launch of gpc_eval with CUDA events on the context's
  * stream; after an evaluation gpc_last_gemm_profile reports the summed kernel time, launch count and executed flops */

@@ -26,7 +26,10 @@ def run(tag, reps):
         t0 = time.time()
         g, ll = gp.logLikelihoodGradient()
         ts.append(time.time() - t0)
-    print("   times ms:", " ".join("%.1f" % (t * 1e3) for t in ts), flush=True)
+    import ctypes as _C
+    enq = _C.c_double(0)
+    check(L.gpc_last_enqueue_ms(gp.ctx.handle, _C.byref(enq)))
+    print("   times ms:", " ".join("%.1f" % (t * 1e3) for t in ts), " host enqueue ms: %.2f" % enq.value, flush=True)
     return min(ts[1:] or ts), g, ll, gp.timings()
 
 
