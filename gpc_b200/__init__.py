@@ -7,3 +7,4 @@ from .kern import (CKern, CWhiteKern, CBiasKern, CRbfKern, CRbfardKern, CMatern3
                    CPolyKern, CCmpndKern, DeviceContext, make_kern)
 from .gp import CGp, CGplvm  # noqa: F401
 from . import matrix  # noqa: F401
+from .io import read_svml  # noqa: F401

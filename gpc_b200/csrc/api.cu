@@ -1056,6 +1056,16 @@ int gpc_last_timings(gpc_ctx* c, double* ms6) {
   for (int i = 0; i < 6; i++) ms6[i] = c->last_ms[i];
   return GPC_OK;
 }
+int gpc_ctx_dims(gpc_ctx* c, int64_t* N, int* D, int* d) {
+  if (!c || !c->haveX || !c->haveM) {
+    set_error("gpc_ctx_dims: X and m have not been set");
+    return GPC_ERR_STATE;
+  }
+  if (N) *N = c->N;
+  if (D) *D = c->D;
+  if (d) *d = c->d;
+  return GPC_OK;
+}
 int gpc_last_enqueue_ms(gpc_ctx* c, double* ms) {
   if (!c || !ms) return GPC_ERR_ARG;
   *ms = c->enqueue_ms;

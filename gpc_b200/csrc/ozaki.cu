@@ -461,24 +461,25 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     const int row = warp * 32 + lane;
     const double rs = a.scaleA[m0 + row] * (1.0 / 4096.0);  // 2^-12: weight of level c = 2
     const double alpha = a.alpha, beta = a.beta;
-    while (!oz_mbar_try_wait(TMEM_FULL, 0)) __nanosleep(256);  // stay out of the issuer's way while the tile is computed
-    oz_tc_fence_after();
+    // the whole C row segment of this thread (64 doubles) is fetched while the tile is still being accumulated: a
+    // load issued per chunk after the wait costs a DRAM round trip per chunk on every tile
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     double* crow = a.C + (int64_t)(m0 + row) + (int64_t)n0 * a.ldc;
-#pragma unroll 1
+    double cv[OZ_BN];
+    if (beta != 0.0) {
+#pragma unroll
+      for (int j = 0; j < OZ_BN; j++) cv[j] = __ldcg(crow + (int64_t)j * a.ldc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < OZ_BN; j++) cv[j] = 0.0;
+    }
+    while (!oz_mbar_try_wait(TMEM_FULL, 0)) __nanosleep(256);  // stay out of the issuer's way while the tile is computed
+    oz_tc_fence_after();
+#pragma unroll
     for (int ch = 0; ch < OZ_BN / 16; ch++) {
-      double acc[16], cv[16];
+      double acc[16];
       int r[16];
       double* cp = crow + (int64_t)(ch * 16) * a.ldc;
-      // all C loads of the chunk first (independent, in flight while the levels are combined): a load placed after the
-      // previous column's store could not be hoisted above it (possible aliasing) and would serialise 64 round trips
-      if (beta != 0.0) {
-#pragma unroll
-        for (int j = 0; j < 16; j++) cv[j] = __ldcg(cp + (int64_t)j * a.ldc);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; j++) cv[j] = 0.0;
-      }
       oz_tmem_ld16(trow + (uint32_t)((S - 1) * OZ_BN + ch * 16), r);
 #pragma unroll
       for (int j = 0; j < 16; j++) acc[j] = (double)r[j];
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         const double v = alpha * (acc[j] * rs * s_cscale[ch * 16 + j]);
-        cp[(int64_t)j * a.ldc] = fma(beta, cv[j], v);
+        cp[(int64_t)j * a.ldc] = fma(beta, cv[ch * 16 + j], v);
       }
     }
   }

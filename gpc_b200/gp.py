@@ -100,6 +100,24 @@ class CGp:
         from .optim import scgOptimise
         return scgOptimise(self, maxIters=iters, verbosity=verbosity, log=log)
 
+    def optimiseNative(self, iters=1000, paramTol=1e-6, objectiveTol=1e-6, log=None):
+        """The same SCG loop run natively inside the library (gpc_gp_optimise_scg): no Python between evaluations.
+        Returns (iterations, device evaluations)."""
+        arr, n, keep = self.pkern._kcomps()
+        trace = np.zeros(max(int(iters), 1))
+        it, ev = C.c_int(0), C.c_int(0)
+        rc = check(lib().gpc_gp_optimise_scg(self.ctx.handle, arr, n, int(iters), paramTol, objectiveTol, ptr(trace),
+                                             C.byref(it), C.byref(ev)))
+        # the library wrote the optimum into the parameter arrays it was given: copy back into the kernel objects
+        for k, pvals in zip(self.pkern._components(), keep):
+            k.params = np.array(pvals, dtype=np.float64)
+        self.KupToDate = False
+        if log is not None:
+            log.extend(trace[:it.value].tolist())
+        if rc > 0:
+            raise _lib.MatrixNonPosDef(rc)
+        return it.value, ev.value
+
     def posteriorMeanVar(self, Xs):
         """mu, var at Xs with output scale/bias applied (CGp.cpp:561-573, 618-623)."""
         self._eval()

@@ -212,6 +212,24 @@ int gpc_bench_leaf(int device, int reps, double* us, long long* stamps);
 int gpc_bench_gemm(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, int reps,
                    double* ms);
 
+/* ---- the callers either side of the path ----------------------------------------------- */
+/* sizes of the problem currently loaded into the context */
+int gpc_ctx_dims(gpc_ctx* ctx, int64_t* N, int* D, int* dout);
+/* Scaled conjugate gradients on the kernel hyper-parameters of an FTC GP: CGp::optimise -> COptimisable::scgOptimise
+ * (COptimisable.cpp:246-396; same steps, same quirks: CGp.cpp:1537-1553).  comps[].params (NATURAL values, must point to
+ * writable memory) are the start point and receive the result; the search runs in the reference's transformed space
+ * (exp / sigmoid, CTransform.cpp:25-112).  trace (may be NULL, max_iters doubles) receives the objective
+ * -log p(y|X,theta) after every iteration.  One device evaluation per distinct point: the reference's second
+ * factorisation at an accepted point (COptimisable.cpp:333 then :347) is served from the first.
+ * Returns 0, or gpc_eval's code if an evaluation failed (the parameters then hold the last accepted point). */
+int gpc_gp_optimise_scg(gpc_ctx* ctx, gpc_kcomp* comps, int ncomp, int max_iters, double param_tol, double obj_tol,
+                        double* trace, int* iters_out, int* evals_out);
+/* SVM-light files as CClctrl::readSvmlDataFile reads them (CClctrl.cpp:55-171): label first, then 1-based index:value
+ * pairs separated by single spaces, '#' lines skipped, '\r' dropped; D = the largest index in the file.
+ * gpc_svml_dims sizes the buffers; gpc_svml_read fills X (nrows x ncols, column-major, ld ldx, zero where absent) and y. */
+int gpc_svml_dims(const char* path, int64_t* nrows, int* ncols);
+int gpc_svml_read(const char* path, double* X, int64_t ldx, double* y, int64_t nrows, int ncols);
+
 /* ---- fp64 GEMM engine selection -------------------------------------------------------------------- */
 /* The dsyrk_/dgemm_ work below dpotrf_/dpotri_ (lapack.h:59-73) runs on one of two engines:
  *   DMMA  : mma.sync.m8n8k4.f64 (the fp64 tensor pipe, 37 TFLOP/s peak);

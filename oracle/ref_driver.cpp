@@ -18,6 +18,8 @@
 #include "CGplvm.h"
 #include "CNoise.h"
 #include "CMatrix.h"
+#include "CClctrl.h"
+#include "COptimisable.h"
 
 extern "C" {
 void scipy_openblas_set_num_threads(int);
@@ -434,6 +436,57 @@ int ref_gplvm_initX(const double* Y, int N, int q, int dout, double* Xout) {
   memcpy(Xout, model.pX->getVals(), sizeof(double) * (size_t)N * q);
   // kern (and its clones) leaked on purpose, see makeKern
   return 0;
+  REF_CATCH
+}
+
+// The reference's SVM-light reader (CClctrl::readSvmlDataFile, CClctrl.cpp:55-171).  X == NULL: sizes only.
+int ref_svml_read(const char* path, int* n, int* d, double* X, double* y) {
+  REF_TRY
+  struct Ctl : public CClctrl {  // CClctrl is abstract only in its help texts (CClctrl.h:50-51)
+    Ctl(int c, char** v) : CClctrl(c, v) {}
+    void helpInfo() {}
+    void helpHeader() {}
+  };
+  char arg0[] = "ref";
+  char* argv[] = {arg0, 0};
+  Ctl ctl(1, argv);
+  CMatrix Xm, ym;
+  ctl.readSvmlDataFile(Xm, ym, std::string(path));
+  *n = (int)Xm.getRows();
+  *d = (int)Xm.getCols();
+  if (X) memcpy(X, Xm.getVals(), sizeof(double) * (size_t)Xm.getRows() * Xm.getCols());
+  if (y) memcpy(y, ym.getVals(), sizeof(double) * (size_t)ym.getRows());
+  return 0;
+  REF_CATCH
+}
+
+// CGp::optimise (SCG, the default optimiser of `gp learn`, gp.cpp:404) for `iters` iterations from the given
+// transformed parameters; returns the transformed parameters and the final log-likelihood.
+int ref_gp_optimise(int ncomp, const int* types, const double* tparams, const double* X, const double* y, int N, int D,
+                    int dout, const double* bias, const double* scale, int iters, double* out_tparams, double* out_ll) {
+  REF_TRY
+  CCmpndKern* kern = makeKern(ncomp, types, tparams, D);
+  if (!kern) return -1;
+  CMatrix Xm(N, D, const_cast<double*>(X));
+  CMatrix ym(N, dout, const_cast<double*>(y));
+  CGaussianNoise noise(&ym);
+  CMatrix nbias(1, dout, 0.0);
+  noise.setBias(nbias);
+  CGp model(kern, &noise, &Xm, CGp::FTC, 0, 0);  // verbosity 0: no display / checkGradients
+  model.setBetaVal(1);
+  CMatrix sc(1, dout, const_cast<double*>(scale));
+  CMatrix bi(1, dout, const_cast<double*>(bias));
+  model.setScale(sc);
+  model.setBias(bi);
+  model.updateM();
+  model.setDefaultOptimiser(CGp::SCG);  // gp.cpp:393-394
+  model.optimise(iters);                // setMaxIters + runDefaultOptimiser (CGp.cpp:1537-1553)
+  unsigned int P = kern->getNumParams();
+  CMatrix tp(1, P);
+  kern->getTransParams(tp);
+  for (unsigned int i = 0; i < P; i++) out_tparams[i] = tp.getVal(0, i);
+  *out_ll = model.logLikelihood();
+  return (int)P;
   REF_CATCH
 }
 

@@ -230,3 +230,30 @@ def gplvm_initX(Y, q):
     X = np.zeros((N, q), order="F")
     _chk(lib().ref_gplvm_initX(_d(Y), N, q, d, _d(X)))
     return X
+
+
+def svml_read(path):
+    """CClctrl::readSvmlDataFile (CClctrl.cpp:55-171) of the compiled reference: (X, y)."""
+    L = lib()
+    n, d = C.c_int(0), C.c_int(0)
+    _chk(L.ref_svml_read(path.encode(), C.byref(n), C.byref(d), None, None))
+    X = np.zeros((n.value, d.value), order="F")
+    y = np.zeros((n.value, 1), order="F")
+    _chk(L.ref_svml_read(path.encode(), C.byref(n), C.byref(d), _d(X), _d(y)))
+    return X, y
+
+
+def gp_optimise(types, tparams, X, y, iters, bias=None, scale=None):
+    """CGp::optimise with SCG (gp learn's default) for `iters` iterations: (transformed parameters, log-likelihood)."""
+    L = lib()
+    X, y = _f(X), _f(y)
+    N, D = X.shape
+    dout = y.shape[1]
+    codes, tp = _spec(types, tparams)
+    bias = np.zeros(dout) if bias is None else np.asarray(bias, dtype=np.float64).ravel()
+    scale = np.ones(dout) if scale is None else np.asarray(scale, dtype=np.float64).ravel()
+    out = np.zeros(tp.size)
+    ll = C.c_double(0)
+    _chk(L.ref_gp_optimise(len(codes), codes.ctypes.data_as(_ip), _d(tp), _d(X), _d(y), N, D, dout,
+                           _d(bias), _d(scale), int(iters), _d(out), C.byref(ll)))
+    return out, ll.value
