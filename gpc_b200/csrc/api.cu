@@ -229,6 +229,10 @@ static int winv_offdiag(const Dense& d, const double* A, int64_t lda, int64_t n1
 }
 
 int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, double* T, bool defer_top) {
+  // at the top level (defer_top) W21 waits for the inverse; its first factor T = L21 W11 is still started here on a
+  // side stream when the caller announced that the inverse follows (d.top_t_ready): one full-GPU product that fills the
+  // idle SMs of the latency-bound A22 recursion
+  const bool eager_t = !defer_top || (d.top_t_ready != nullptr);
   double* W = d.Winv + base + base * d.ldw;
   if (n == TILE)
     return launch_potrf_leaf(A, lda, nullptr, d.info, (int)base, d.nvalid - base, d.logdet, d.s, d.launches, W, d.ldw);
@@ -244,7 +248,7 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
   }
   cudaEvent_t t_ready = nullptr;
   bool t_done = false;
-  if (!defer_top && d.fk) {  // T on a side stream, concurrent with the SYRK and the A22 recursion
+  if (eager_t && d.fk) {  // T on a side stream, concurrent with the SYRK and the A22 recursion
     cudaEvent_t e1 = d.fk->event();
     t_ready = d.fk->event();
     Dense ds = d;
@@ -262,14 +266,19 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
     GPC_CHECK(gemm(d, g));
   }
   GPC_CHECK(potrf_inv_rec(d, A22, lda, n2, base + n1, T + (size_t)n1 * n2, false));
-  if (defer_top) return GPC_OK;
+  if (defer_top) {
+    if (d.top_t_ready) *d.top_t_ready = t_done ? t_ready : nullptr;
+    return GPC_OK;
+  }
   return winv_offdiag(d, A, lda, n1, n2, base, T, t_done, t_ready);
 }
 
 int inverse_from_W(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, bool deferred_top) {
   if (deferred_top && n > TILE) {
     int64_t n1 = split(n), n2 = n - n1;
-    GPC_CHECK(winv_offdiag(d, L, ldl, n1, n2, 0, d.Tpool, false, nullptr));
+    const cudaEvent_t t_ready = d.top_t_ready ? *d.top_t_ready : nullptr;  // T already queued by the factorisation?
+    GPC_CHECK(winv_offdiag(d, L, ldl, n1, n2, 0, d.Tpool, t_ready != nullptr, t_ready));
+    if (d.top_t_ready) *d.top_t_ready = nullptr;
   }
   // Out(i, j) = sum_{kk >= i} W(kk, i) W(kk, j), i >= j: lower tiles only, k starts at the tile's first row
   GemmCall g{d.Winv, d.Winv, Out, d.ldw, d.ldw, ldo, n, n, n, 1.0, 0.0, true, true, true};
@@ -295,6 +304,8 @@ struct gpc_ctx {
   double *X, *M, *alpha, *K, *L, *Kinv, *W, *Dinv;
   double* Winv;    // W = L^-1 (lower block triangle), built by potrf_inv_rec; Kinv doubles as its scratch (tmpL, Tpool)
   bool w_deferred; // the top-level W21 has not been formed yet
+  bool inverse_follows;        // set by gpc_eval: the factorisation may start the top-level T early
+  cudaEvent_t top_t_ready;     // non-null: T of the top level is being computed on a side stream
   int64_t winv_np; // padded size for which the diagonal blocks of Winv have zero strict upper parts (0: never)
   bool use_winv;   // GPC_POTRF_MODE != "rec": factor + explicit inverse (default); "rec": recursive TRSM / Schur inverse
   double* scal;    // device scalars: [0] logdet [1] quad [2] trace ; then g[GPC_MAX_PARAMS]
@@ -334,6 +345,7 @@ static Dense dense_of(gpc_ctx* c) {
   d.W = c->W;
   d.nvalid = c->N;
   d.Winv = c->Winv;
+  d.top_t_ready = nullptr;
   d.ldw = c->Np;
   // scratch inside the (not yet written) K^-1 buffer: tmpL then Tpool
   d.tmpL = c->Kinv;
@@ -613,6 +625,10 @@ static int potrf_async(gpc_ctx* c) {
     }
     Dense d = dense_of(c);
     c->w_deferred = true;
+    c->top_t_ready = nullptr;
+    // only where the factorisation is latency-bound (idle SMs to fill); at N = 32768 two concurrent large products
+    // just contend for L2
+    if (c->inverse_follows && c->Np <= 16384) d.top_t_ready = &c->top_t_ready;
     return potrf_inv_rec(d, c->L, c->Np, c->Np, 0, d.Tpool, true);
   }
   Dense d = dense_of(c);
@@ -622,6 +638,7 @@ static int potrf_async(gpc_ctx* c) {
 static int inverse_async(gpc_ctx* c) {
   Dense d = dense_of(c);
   if (c->use_winv) {
+    d.top_t_ready = &c->top_t_ready;
     GPC_CHECK(inverse_from_W(d, c->L, c->Np, c->Np, c->Kinv, c->Np, c->w_deferred));
     c->w_deferred = false;
     return GPC_OK;
@@ -946,7 +963,10 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
       c->prof->flops.clear();
       c->prof->recs.clear();
     }
-    GPC_CHECK(potrf_async(c));
+    c->inverse_follows = true;
+    int prc = potrf_async(c);
+    c->inverse_follows = false;
+    GPC_CHECK(prc);
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[2], s));
     GPC_CHECK(trace_phase(c, "potrf"));
     // optimistic: queue the rest before looking at info (a failed factorisation is rare and just redone)

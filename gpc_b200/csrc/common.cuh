@@ -127,6 +127,7 @@ struct Dense {
   int64_t ldw = 0;
   double* tmpL = nullptr;  // >= (n/2 + TILE) * (n/2) doubles: out-of-place result of a panel solve
   double* Tpool = nullptr; // >= tspace(n_total) doubles: T = L21 W11 per recursion depth
+  cudaEvent_t* top_t_ready = nullptr;  // where the event of an early top-level T product is left for inverse_from_W
   // inverse of the diagonal block of the factor at row/column dbase: the diagonal block of W when W is kept, else Dinv
   const double* dinv_blk(int64_t dbase, int64_t* ld) const {
     if (Winv) {

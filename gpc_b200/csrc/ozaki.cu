@@ -565,7 +565,9 @@ struct OzWorkspace {
   bool used = false;
 };
 static std::mutex g_oz_mu;
-static OzWorkspace g_oz_ws[64];
+constexpr int OZ_BIG = 2;  // two large calls (e.g. main stream + one side stream) may be in flight
+static OzWorkspace g_oz_ws[64][OZ_BIG];
+static unsigned g_oz_big_next[64];
 // Calls whose slices fit OZ_SMALL_BYTES per operand take one of OZ_POOL fixed-size workspaces round-robin instead (each
 // guarded by its own event), so that the concurrent branches of the recursions (fork/join side streams) do not
 // serialise on the shared buffers.  The pool is allocated once per device: no allocation in steady state.
@@ -705,7 +707,7 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   const int S = (slices >= 2 && slices <= OZ_MAXS) ? slices : g_oz_S;
   const size_t op_bytes = (size_t)S * (size_t)(c.m > c.n ? c.m : c.n) * (size_t)c.k;
   const bool shared_ws = op_bytes > OZ_SMALL_BYTES;
-  OzWorkspace& w = shared_ws ? g_oz_ws[dev] : g_oz_pool[dev][g_oz_pool_next[dev]++ % OZ_POOL];
+  OzWorkspace& w = shared_ws ? g_oz_ws[dev][g_oz_big_next[dev]++ % OZ_BIG] : g_oz_pool[dev][g_oz_pool_next[dev]++ % OZ_POOL];
   if (!shared_ws && !w.sl[0]) {  // first small call on this device: allocate the whole pool now, not over 8 calls
     for (int q = 0; q < OZ_POOL; q++)
       for (int i = 0; i < 2; i++) GPC_CHECK(ensure_ws(g_oz_pool[dev][q], i, OZ_SMALL_BYTES, OZ_SMALL_ROWS));
@@ -779,15 +781,17 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
 void oz_release_device(int dev) {
   if (dev < 0 || dev >= 64) return;
   std::lock_guard<std::mutex> lk(g_oz_mu);
-  OzWorkspace& w = g_oz_ws[dev];
-  for (int i = 0; i < 2; i++) {
-    if (w.sl[i]) cudaFree(w.sl[i]);
-    if (w.emax[i]) cudaFree(w.emax[i]);
-    if (w.scale[i]) cudaFree(w.scale[i]);
+  for (int b = 0; b < OZ_BIG; b++) {
+    OzWorkspace& w = g_oz_ws[dev][b];
+    for (int i = 0; i < 2; i++) {
+      if (w.sl[i]) cudaFree(w.sl[i]);
+      if (w.emax[i]) cudaFree(w.emax[i]);
+      if (w.scale[i]) cudaFree(w.scale[i]);
+    }
+    if (w.errflag) cudaFree(w.errflag);
+    if (w.done) cudaEventDestroy(w.done);
+    w = OzWorkspace();
   }
-  if (w.errflag) cudaFree(w.errflag);
-  if (w.done) cudaEventDestroy(w.done);
-  w = OzWorkspace();
   for (int q = 0; q < OZ_POOL; q++) {
     OzWorkspace& v = g_oz_pool[dev][q];
     for (int i = 0; i < 2; i++) {
