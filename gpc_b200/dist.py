@@ -3,12 +3,13 @@ in libgpc_b200.so through the device-level C ABI (gpc_dev_*).  SURVEY.md 8(e).
 
 Layout: the N x N problem is split into block columns of width NB, dealt round-robin to the ranks (1-D block-cyclic).
   K build      each rank builds its own block columns (no communication; X replicated)
-  potrf        right-looking: the owner factors the diagonal block + solves the panel below (gpc_dev_potrf /
-               gpc_dev_trsm), BROADCASTS the panel (+ the inverses of its 128-blocks) to everybody, every rank applies
-               the rank-NB update to the block columns it owns (gpc_dev_gemm).  After the loop every rank holds all of L.
-  inverse      W = L^-1 by block columns: the owner solves W_J' L_sub' = [I 0] (N^3/3 flop in total, split over ranks),
-               the W_J' blocks are ALL-GATHERED, then each rank forms its own block columns of
-               K^-1 = W'W as GEMMs (another N^3/3 split over ranks)
+  potrf        right-looking with a look-ahead of one panel: the owner factors the diagonal block + solves the panel
+               below (gpc_dev_potrf / gpc_dev_trsm) and BROADCASTS the panel (+ the inverses of its 128-blocks)
+               asynchronously; every rank applies the rank-NB update to the block columns it owns (gpc_dev_gemm), the
+               owner of the next panel to that column first.  After the loop every rank holds all of L.
+  inverse      W = L^-1 by block columns: every rank solves W_J' L_sub' = [I 0] for ALL its own block columns first
+               (N^3/3 flop in total, split over ranks, no communication), then the W_J' blocks are ALL-GATHERED, then
+               each rank forms its own block columns of K^-1 = W'W as GEMMs (another N^3/3 split over ranks)
   alpha        two triangular solves with the replicated L (O(N^2 d), every rank)
   gradient     fused pass over the owned block columns of K^-1 (gpc_dev_grad_cols), ALL-REDUCE of P doubles;
                logdet partials all-reduced likewise
@@ -207,26 +208,42 @@ class DistGp:
         for b in self.owned:
             ops.kbuild_cols(kc, self.Xt, self.N, self.Lt, b * NB, NB)
         self._tick("kbuild")
-        # ---- right-looking Cholesky with panel broadcasts
-        for kb in range(nblk):
+        # ---- right-looking Cholesky with panel broadcasts and a look-ahead of one panel: the owner of panel kb+1
+        #      updates that block column first, factors it and starts its (asynchronous) broadcast while everybody is
+        #      still applying panel kb to the rest of their columns
+        def start_panel(kb):
             k0 = kb * NB
             src = self.owner(kb)
             if self.rank == src:
                 ops.potrf_block(self.Lt, k0, NB, self.N, self.Dinv.view(-1))
                 ops.trsm_panel(self.Lt, k0, NB, self.Dinv.view(-1))
-            self._tick("potrf_panel")
-            if self.world > 1:
-                panel = self.Lt[k0:k0 + NB, k0:]            # nb block-column, rows k0.. (strided view)
-                buf = panel.contiguous() if self.rank == src else ops.empty(NB, Np - k0)
-                self._bcast(buf, src)
-                dblk = self.Dinv[k0 // 128:(k0 + NB) // 128]
-                self._bcast(dblk, src)
-                if self.rank != src:
-                    panel.copy_(buf)
-                del buf
+            if self.world == 1:
+                return None, None, []
+            panel = self.Lt[k0:k0 + NB, k0:]            # nb block-column, rows k0.. (strided view)
+            buf = panel.contiguous() if self.rank == src else ops.empty(NB, Np - k0)
+            dblk = self.Dinv[k0 // 128:(k0 + NB) // 128]
+            works = [dist.broadcast(buf, src=src, group=self.group, async_op=True),
+                     dist.broadcast(dblk, src=src, group=self.group, async_op=True)]
+            return panel, buf, works
+
+        pending = start_panel(0)
+        self._tick("potrf_panel")
+        for kb in range(nblk):
+            k0 = kb * NB
+            panel, buf, works = pending
+            for w in works:
+                w.wait()
+            if works and self.rank != self.owner(kb):
+                panel.copy_(buf)
+            del buf, panel
             self._tick("potrf_bcast")
+            if kb + 1 < nblk:
+                if self.rank == self.owner(kb + 1):
+                    ops.update_cols(self.Lt, (kb + 1) * NB, NB, k0, NB)
+                pending = start_panel(kb + 1)
+                self._tick("potrf_panel")
             for b in self.owned:
-                if b > kb:
+                if b > kb + 1:
                     ops.update_cols(self.Lt, b * NB, NB, k0, NB)
             self._tick("potrf_update")
         # ---- status: first non-positive pivot (max over ranks of a "first or zero" is good enough to fail loudly)
@@ -240,16 +257,22 @@ class DistGp:
         ld_t = st[1:].clone()
         self._allreduce(ld_t)
         logdet = float(ld_t.item())
-        # ---- W = L^-1 by block columns, all-gathered (broadcast of the compact non-zero part of every block)
+        # ---- W = L^-1 by block columns.  Every rank first solves ALL the block columns it owns (no communication:
+        #      the ranks work concurrently), only then are the compact non-zero parts all-gathered by broadcasts.
+        #      (Solving and broadcasting block by block serialises the ranks: the owner of block b+1 sits in the
+        #      broadcast of block b while its peer is still solving.)
+        mine = {}
+        for b in self.owned:
+            mine[b] = ops.winv_block(self.Lt, b * NB, NB, self.Dinv.view(-1))
+        self._tick("winv_solve")
         for b in range(nblk):
             j0 = b * NB
             src = self.owner(b)
-            buf = ops.winv_block(self.Lt, j0, NB, self.Dinv.view(-1)) if self.rank == src else ops.empty(NB, Np - j0)
-            self._tick("winv_solve")
+            buf = mine.pop(b) if self.rank == src else ops.empty(NB, Np - j0)
             self._bcast(buf, src)
             self.Wc[j0:j0 + NB, j0:].copy_(buf)
             del buf
-            self._tick("winv_bcast")
+        self._tick("winv_bcast")
         # ---- own block columns of K^-1 = W'W (rows i >= j0)
         for jl, b in enumerate(self.owned):
             ops.kinv_cols(self.Kc, self.Wc, b * NB, NB, jl * NB)
