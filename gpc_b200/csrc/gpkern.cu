@@ -231,7 +231,7 @@ __device__ __forceinline__ void tri_tile(int64_t t, int& bi, int& bj) {
 
 // ---- K build: lower-triangle 64x64 tiles (bi >= bj).  Diagonal entries follow diagComputeElement
 // (CKern.cpp:165-171): the generic value at r = 0 plus the white variances.  Rows/cols >= n: identity.
-__global__ void __launch_bounds__(KTHREADS) kbuild_kernel(const __grid_constant__ KSpec ks, const double* __restrict__ X,
+__global__ void __launch_bounds__(KTHREADS, 2) kbuild_kernel(const __grid_constant__ KSpec ks, const double* __restrict__ X,
                                                          int64_t ldx, int64_t n, double* __restrict__ K, int64_t ldk) {
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) uint64_t bar;
@@ -391,7 +391,7 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(KTHREADS) grad_kernel(const __grid_constant__ KSpec ks, const double* __restrict__ X,
+__global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant__ KSpec ks, const double* __restrict__ X,
                                                        int64_t ldx, int64_t n, int64_t ntiles_edge, int64_t tc0,
                                                        int64_t tc1, const double* __restrict__ Cg, int64_t ldc,
                                                        const double* __restrict__ alpha, int64_t lda, int dout,
