@@ -707,7 +707,11 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   const int S = (slices >= 2 && slices <= OZ_MAXS) ? slices : g_oz_S;
   const size_t op_bytes = (size_t)S * (size_t)(c.m > c.n ? c.m : c.n) * (size_t)c.k;
   const bool shared_ws = op_bytes > OZ_SMALL_BYTES;
-  OzWorkspace& w = shared_ws ? g_oz_ws[dev][g_oz_big_next[dev]++ % OZ_BIG] : g_oz_pool[dev][g_oz_pool_next[dev]++ % OZ_POOL];
+  // the second large workspace only for operands up to 1 GB of slices: beyond that (N >= 32768) large calls are
+  // serialised through one workspace, which keeps N = 65536 within one GPU's memory
+  const bool rotate_big = op_bytes <= ((size_t)1 << 30);
+  OzWorkspace& w = shared_ws ? g_oz_ws[dev][rotate_big ? (g_oz_big_next[dev]++ % OZ_BIG) : 0]
+                             : g_oz_pool[dev][g_oz_pool_next[dev]++ % OZ_POOL];
   if (!shared_ws && !w.sl[0]) {  // first small call on this device: allocate the whole pool now, not over 8 calls
     for (int q = 0; q < OZ_POOL; q++)
       for (int i = 0; i < 2; i++) GPC_CHECK(ensure_ws(g_oz_pool[dev][q], i, OZ_SMALL_BYTES, OZ_SMALL_ROWS));
