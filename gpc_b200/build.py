@@ -11,6 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpc_b200.so")
+SHIM = os.path.join(HERE, "libgpc_lapack_shim.so")
 SOURCES = ["dense.cu", "ozaki.cu", "gpkern.cu", "api.cu", "lapack_api.cu", "api_dev.cu", "host.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "gpc_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -45,6 +46,12 @@ def build(force=False, verbose=False):
     if force or procs or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         subprocess.check_call(cmd)
+    # the Fortran-ABI shim (dpotrf_, dpotri_, dtrsm_, dsyrk_, dgemm_ -> gpc_d*): link or LD_PRELOAD it in front of a
+    # BLAS and the unmodified reference objects run those calls on the GPU (level 0)
+    shim_src = os.path.join(CSRC, "lapack_shim.cpp")
+    if force or _stale(SHIM, [shim_src, LIB] + HEADERS):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-o", SHIM, shim_src,
+                               "-L" + HERE, "-lgpc_b200", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

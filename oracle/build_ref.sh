@@ -43,4 +43,26 @@ COMMON="CClctrl.o CMatrix.o ndlfortran.o lbfgs_stub.o CNoise.o ndlutil.o ndlstru
 g++ -shared -o "$OUT/libgpcref.so" ref_driver.o CGp.o CGplvm.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
 g++ -o "$OUT/gp" gp.o CGp.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
 g++ -o "$OUT/gplvm" gplvm.o CGplvm.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
+# ---- the UNMODIFIED reference with its five hot BLAS/LAPACK calls resolved by the B200 library (seam (1)):
+# same sources, same flags, but dpotrf_/dpotri_/dtrsm_/dsyrk_/dgemm_ keep their plain Fortran names and are taken from
+# gpc_b200/libgpc_lapack_shim.so; everything else still comes from OpenBLAS.  Built only when the shim exists.
+SHIMDIR="$(cd "$HERE/../gpc_b200" && pwd)"
+if [ -f "$SHIMDIR/libgpc_lapack_shim.so" ]; then
+  mkdir -p "$OUT/obj_b200"
+  grep -v -E "define (dpotrf|dpotri|dtrsm|dsyrk|dgemm)_ " "$OUT/obj/blasmap.h" > "$OUT/obj_b200/blasmap.h"
+  CXXB="-std=gnu++98 -O3 -fPIC -w -D_LINUX -include $OUT/obj_b200/blasmap.h -I$REF"
+  pids=()
+  for f in CClctrl CGp CMatrix CNoise ndlutil ndlstrutil CTransform COptimisable CKern CDist ndlassert gp; do
+    if [ ! -f "$OUT/obj_b200/$f.o" ] || [ "$REF/$f.cpp" -nt "$OUT/obj_b200/$f.o" ]; then
+      g++ $CXXB -c "$REF/$f.cpp" -o "$OUT/obj_b200/$f.o" &
+      pids+=($!)
+    fi
+  done
+  for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+  cd "$OUT/obj_b200"
+  g++ -o "$OUT/gp_b200" gp.o CGp.o CClctrl.o CMatrix.o ../obj/ndlfortran.o ../obj/lbfgs_stub.o CNoise.o ndlutil.o ndlstrutil.o \
+      CTransform.o COptimisable.o CKern.o CDist.o ndlassert.o -L"$SHIMDIR" -lgpc_lapack_shim -lgpc_b200 "$OB" \
+      -Wl,-rpath,"$SP" -Wl,-rpath,'$ORIGIN/../../gpc_b200' -lm
+  echo "build_ref: built $OUT/gp_b200 (reference objects + gpc_b200 Fortran shim)"
+fi
 echo "build_ref: built $OUT/libgpcref.so, gp, gplvm (OpenBLAS: $OB)"

@@ -90,3 +90,15 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no numpy fallback", ""), f + " references the oracle"
                 assert "libgpcref" not in src
+
+
+def test_fortran_shim_exports_the_lapack_h_symbols():
+    """gpc_b200/libgpc_lapack_shim.so carries the five hot Fortran symbols of the reference's lapack.h:59-73, 186-222
+    under their own names, so it can be linked or preloaded in front of a BLAS (level 0)."""
+    import ctypes as C
+    import gpc_b200
+    shim = os.path.join(os.path.dirname(gpc_b200.LIB_PATH), "libgpc_lapack_shim.so")
+    assert os.path.exists(shim), "run python -m gpc_b200.build"
+    L = C.CDLL(shim)
+    for name in ("dpotrf_", "dpotri_", "dtrsm_", "dsyrk_", "dgemm_"):
+        assert hasattr(L, name), name
