@@ -52,7 +52,7 @@ if [ -f "$SHIMDIR/libgpc_lapack_shim.so" ]; then
   grep -v -E "define (dpotrf|dpotri|dtrsm|dsyrk|dgemm)_ " "$OUT/obj/blasmap.h" > "$OUT/obj_b200/blasmap.h"
   CXXB="-std=gnu++98 -O3 -fPIC -w -D_LINUX -include $OUT/obj_b200/blasmap.h -I$REF"
   pids=()
-  for f in CClctrl CGp CMatrix CNoise ndlutil ndlstrutil CTransform COptimisable CKern CDist ndlassert gp; do
+  for f in CClctrl CGp CGplvm CMatrix CNoise ndlutil ndlstrutil CTransform COptimisable CKern CDist ndlassert gp gplvm; do
     if [ ! -f "$OUT/obj_b200/$f.o" ] || [ "$REF/$f.cpp" -nt "$OUT/obj_b200/$f.o" ]; then
       g++ $CXXB -c "$REF/$f.cpp" -o "$OUT/obj_b200/$f.o" &
       pids+=($!)
@@ -63,6 +63,9 @@ if [ -f "$SHIMDIR/libgpc_lapack_shim.so" ]; then
   g++ -o "$OUT/gp_b200" gp.o CGp.o CClctrl.o CMatrix.o ../obj/ndlfortran.o ../obj/lbfgs_stub.o CNoise.o ndlutil.o ndlstrutil.o \
       CTransform.o COptimisable.o CKern.o CDist.o ndlassert.o -L"$SHIMDIR" -lgpc_lapack_shim -lgpc_b200 "$OB" \
       -Wl,-rpath,"$SP" -Wl,-rpath,'$ORIGIN/../../gpc_b200' -lm
-  echo "build_ref: built $OUT/gp_b200 (reference objects + gpc_b200 Fortran shim)"
+  g++ -o "$OUT/gplvm_b200" gplvm.o CGplvm.o CClctrl.o CMatrix.o ../obj/ndlfortran.o ../obj/lbfgs_stub.o CNoise.o ndlutil.o ndlstrutil.o \
+      CTransform.o COptimisable.o CKern.o CDist.o ndlassert.o -L"$SHIMDIR" -lgpc_lapack_shim -lgpc_b200 "$OB" \
+      -Wl,-rpath,"$SP" -Wl,-rpath,'$ORIGIN/../../gpc_b200' -lm
+  echo "build_ref: built $OUT/gp_b200, gplvm_b200 (reference objects + gpc_b200 Fortran shim)"
 fi
 echo "build_ref: built $OUT/libgpcref.so, gp, gplvm (OpenBLAS: $OB)"
