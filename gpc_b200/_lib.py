@@ -30,6 +30,9 @@ class MatrixNonPosDef(GpcError):
         self.info = info
 
 
+OBJECTIVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
+                           C.POINTER(C.c_double))
+
 # every symbol include/gpc_b200.h declares (tests/test_abi_cpu.py checks the .so exports all of them)
 SYMBOLS = [
     "gpc_last_error", "gpc_device_count", "gpc_kern_nparams", "gpc_kern_transform", "gpc_transform_atox",
@@ -39,7 +42,7 @@ SYMBOLS = [
     "gpc_solve_alpha", "gpc_inverse", "gpc_alpha_from_inverse", "gpc_grad", "gpc_kern_grad", "gpc_posterior",
     "gpc_eval", "gpc_download", "gpc_last_timings", "gpc_last_enqueue_ms", "gpc_dpotrf", "gpc_dpotri", "gpc_dtrsm", "gpc_dsyrk",
     "gpc_dgemm", "gpc_dsymv", "gpc_bench_dmma_peak", "gpc_bench_syrk", "gpc_ctx_set_profile", "gpc_last_gemm_profile", "gpc_last_gemm_profile_split", "gpc_bench_gemm", "gpc_dev_create", "gpc_dev_destroy", "gpc_dev_set_stream",
-    "gpc_bench_leaf", "gpc_ctx_dims", "gpc_gp_optimise_scg", "gpc_svml_dims", "gpc_svml_read", "gpc_set_gemm_engine", "gpc_gemm_engine_slices", "gpc_gemm_check", "gpc_oz_slice_check",
+    "gpc_bench_leaf", "gpc_ctx_dims", "gpc_gp_optimise_scg", "gpc_scg_minimise", "gpc_svml_dims", "gpc_svml_read", "gpc_set_gemm_engine", "gpc_gemm_engine_slices", "gpc_gemm_check", "gpc_oz_slice_check",
     "gpc_dev_launch_count", "gpc_dev_potrf", "gpc_dev_trsm", "gpc_dev_gemm", "gpc_dev_kbuild_cols", "gpc_dev_grad_cols",
 ]
 
@@ -118,6 +121,8 @@ def lib():
     L.gpc_ctx_dims.argtypes = [C.c_void_p, C.POINTER(i64), c_int_p, c_int_p]
     L.gpc_gp_optimise_scg.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p,
                                       c_int_p, c_int_p]
+    L.gpc_scg_minimise.argtypes = [OBJECTIVE_FN, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                   C.c_void_p, c_int_p, c_int_p]
     L.gpc_svml_dims.argtypes = [C.c_char_p, C.POINTER(i64), c_int_p]
     L.gpc_svml_read.argtypes = [C.c_char_p, C.c_void_p, i64, C.c_void_p, i64, C.c_int]
     L.gpc_bench_leaf.argtypes = [C.c_int, C.c_int, c_double_p, C.c_void_p]

@@ -53,6 +53,28 @@ struct GpObjective {
   }
 };
 
+// the optimiser sees any model through this pair (COptimisable::computeObjectiveGradParams, COptimisable.h:15-239)
+struct CallbackObjective {
+  gpc_objective_fn fn;
+  void* user;
+  int P;
+  std::vector<double> w_cached, g_cached;
+  double obj_cached;
+  bool have;
+  int evals;
+  void set(const std::vector<double>&) {}
+  int eval(const std::vector<double>& w) {
+    if (have && w == w_cached) return GPC_OK;
+    g_cached.resize((size_t)P);
+    int rc = fn(user, w.data(), P, &obj_cached, g_cached.data());
+    if (rc != GPC_OK) return rc;
+    evals++;
+    w_cached = w;
+    have = true;
+    return GPC_OK;
+  }
+};
+
 double dot(const std::vector<double>& a, const std::vector<double>& b) {
   double s = 0.0;
   for (size_t i = 0; i < a.size(); i++) s += a[i] * b[i];
@@ -102,38 +124,17 @@ extern "C" {
 
 int gpc_ctx_dims(gpc_ctx* c, int64_t* N, int* D, int* d);  // api.cu
 
-// Scaled conjugate gradients (Moller 1993) on the kernel hyper-parameters, step for step COptimisable::scgOptimise
-// including the two quirks that shape its trajectory: step 3 adds lambdaDiff*|p| (not |p|^2) to delta
-// (COptimisable.cpp:313) and the convergence test looks at CMatrix::max(), which as implemented is
-// max(p[0], p[last]) (CMatrix.cpp:568-577).
-int gpc_gp_optimise_scg(gpc_ctx* ctx, gpc_kcomp* comps, int ncomp, int max_iters, double param_tol, double obj_tol,
-                        double* trace, int* iters_out, int* evals_out) {
-  if (!ctx || !comps || ncomp < 1 || max_iters < 0) {
-    set_error("gpc_gp_optimise_scg: bad arguments");
-    return GPC_ERR_ARG;
-  }
-  GpObjective f;
-  f.ctx = ctx;
-  f.comps = comps;
-  f.ncomp = ncomp;
-  f.have = false;
-  f.evals = 0;
-  f.obj_cached = 0.0;
-  int D = 0;
-  if (gpc_ctx_dims(ctx, &f.N, &D, &f.d) != GPC_OK) return GPC_ERR_STATE;
-  for (int c = 0; c < ncomp; c++) {
-    if (comps[c].nparams != gpc_kern_nparams(comps[c].type, D) || !comps[c].params) {
-      set_error("gpc_gp_optimise_scg: component parameter count does not match its type");
-      return GPC_ERR_ARG;
-    }
-    for (int i = 0; i < comps[c].nparams; i++) {
-      f.tr.push_back(gpc_kern_transform(comps[c].type, i));
-      f.slot.push_back(const_cast<double*>(comps[c].params) + i);
-    }
-  }
-  const int nP = f.P = (int)f.slot.size();
-  std::vector<double> w((size_t)nP), wPlus((size_t)nP), r((size_t)nP), p((size_t)nP), s((size_t)nP, 0.0), rp((size_t)nP);
-  for (int i = 0; i < nP; i++) w[i] = gpc_transform_xtoa(f.tr[i], *f.slot[i]);
+// Scaled conjugate gradients (Moller 1993), step for step COptimisable::scgOptimise (COptimisable.cpp:246-396) including
+// the two quirks that shape its trajectory: step 3 adds lambdaDiff*|p| (not |p|^2) to delta (:313) and the
+// convergence test looks at CMatrix::max(), which as implemented is max(p[0], p[last]) (CMatrix.cpp:568-577).
+// F: eval(w) -> rc, then obj_cached / g_cached hold objective and gradient at w (cached per point); set(w).
+}  // extern "C"
+
+namespace {
+template <class F>
+int scg_loop(F& f, std::vector<double>& w, int max_iters, double param_tol, double obj_tol, double* trace, int* iters_out) {
+  const int nP = (int)w.size();
+  std::vector<double> wPlus((size_t)nP), r((size_t)nP), p((size_t)nP), s((size_t)nP, 0.0), rp((size_t)nP);
   const double m_step = 1.0e-4, m_reg = 1.0;
   double lam = m_reg, lamBar = 0.0, delta = 0.0;
   bool success = true;
@@ -194,10 +195,68 @@ int gpc_gp_optimise_scg(gpc_ctx* ctx, gpc_kcomp* comps, int ncomp, int max_iters
       break;
     }
   }
-  f.set(w);  // leave the accepted point in the caller's parameter arrays
+  f.set(w);  // leave the accepted point with the model
   if (iters_out) *iters_out = it - 1 > max_iters ? max_iters : it - 1;
+  return rc;
+}
+}  // namespace
+
+extern "C" {
+
+// any objective through a callback (the GP-LVM's [kernel][X] parameters, tests): w holds the start point and receives
+// the result
+int gpc_scg_minimise(gpc_objective_fn fn, void* user, double* w, int n, int max_iters, double param_tol, double obj_tol,
+                     double* trace, int* iters_out, int* evals_out) {
+  if (!fn || !w || n < 1 || max_iters < 0) {
+    set_error("gpc_scg_minimise: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  CallbackObjective f;
+  f.fn = fn;
+  f.user = user;
+  f.P = n;
+  f.have = false;
+  f.evals = 0;
+  f.obj_cached = 0.0;
+  std::vector<double> wv(w, w + n);
+  int rc = scg_loop(f, wv, max_iters, param_tol, obj_tol, trace, iters_out);
+  for (int i = 0; i < n; i++) w[i] = wv[i];
   if (evals_out) *evals_out = f.evals;
-  return rc < 0 ? rc : (rc > 0 ? rc : GPC_OK);
+  return rc;
+}
+
+// the kernel hyper-parameters of an FTC GP: CGp::optimise (CGp.cpp:1537-1553) with the default optimiser
+int gpc_gp_optimise_scg(gpc_ctx* ctx, gpc_kcomp* comps, int ncomp, int max_iters, double param_tol, double obj_tol,
+                        double* trace, int* iters_out, int* evals_out) {
+  if (!ctx || !comps || ncomp < 1 || max_iters < 0) {
+    set_error("gpc_gp_optimise_scg: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  GpObjective f;
+  f.ctx = ctx;
+  f.comps = comps;
+  f.ncomp = ncomp;
+  f.have = false;
+  f.evals = 0;
+  f.obj_cached = 0.0;
+  int D = 0;
+  if (gpc_ctx_dims(ctx, &f.N, &D, &f.d) != GPC_OK) return GPC_ERR_STATE;
+  for (int c = 0; c < ncomp; c++) {
+    if (comps[c].nparams != gpc_kern_nparams(comps[c].type, D) || !comps[c].params) {
+      set_error("gpc_gp_optimise_scg: component parameter count does not match its type");
+      return GPC_ERR_ARG;
+    }
+    for (int i = 0; i < comps[c].nparams; i++) {
+      f.tr.push_back(gpc_kern_transform(comps[c].type, i));
+      f.slot.push_back(const_cast<double*>(comps[c].params) + i);
+    }
+  }
+  const int nP = f.P = (int)f.slot.size();
+  std::vector<double> w((size_t)nP);
+  for (int i = 0; i < nP; i++) w[i] = gpc_transform_xtoa(f.tr[i], *f.slot[i]);
+  int rc = scg_loop(f, w, max_iters, param_tol, obj_tol, trace, iters_out);
+  if (evals_out) *evals_out = f.evals;
+  return rc;
 }
 
 int gpc_svml_dims(const char* path, int64_t* nrows, int* ncols) {

@@ -75,3 +75,39 @@ def scgOptimise(model, maxIters=1000, paramTol=1e-6, objectiveTol=1e-6, verbosit
         if success and abs(pmax * alpha) < paramTol and abs(newObj - oldObj) < objectiveTol:  # 9
             return it
     return maxIters
+
+
+def scgOptimiseNative(model, maxIters=1000, paramTol=1e-6, objectiveTol=1e-6, log=None):
+    """The same loop run natively (gpc_scg_minimise in libgpc_b200.so): Python is entered once per DISTINCT point, to
+    evaluate objective and gradient together.  Returns (iterations, evaluations)."""
+    import ctypes as C
+
+    from ._lib import OBJECTIVE_FN, check, lib
+
+    w = np.ascontiguousarray(model.getOptParams(), dtype=np.float64)
+    n = w.size
+    err = []
+
+    def fn(user, wp, nn, obj, grad):
+        try:
+            model.setOptParams(np.ctypeslib.as_array(wp, shape=(nn,)).copy())
+            g, f = model.computeObjectiveGradParams()
+            obj[0] = float(f)
+            np.ctypeslib.as_array(grad, shape=(nn,))[:] = np.asarray(g, dtype=np.float64)
+            return 0
+        except Exception as e:  # no exception may cross the C ABI
+            err.append(e)
+            return -1
+
+    cb = OBJECTIVE_FN(fn)
+    trace = np.zeros(max(int(maxIters), 1))
+    it, ev = C.c_int(0), C.c_int(0)
+    rc = lib().gpc_scg_minimise(cb, None, w.ctypes.data_as(C.c_void_p), n, int(maxIters), paramTol, objectiveTol,
+                                trace.ctypes.data_as(C.c_void_p), C.byref(it), C.byref(ev))
+    if err:
+        raise err[0]
+    check(rc)
+    model.setOptParams(w)
+    if log is not None:
+        log.extend(trace[:it.value].tolist())
+    return it.value, ev.value

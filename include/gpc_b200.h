@@ -224,6 +224,11 @@ int gpc_ctx_dims(gpc_ctx* ctx, int64_t* N, int* D, int* dout);
  * Returns 0, or gpc_eval's code if an evaluation failed (the parameters then hold the last accepted point). */
 int gpc_gp_optimise_scg(gpc_ctx* ctx, gpc_kcomp* comps, int ncomp, int max_iters, double param_tol, double obj_tol,
                         double* trace, int* iters_out, int* evals_out);
+/* The same loop for any objective (the COptimisable interface, COptimisable.h:15-239): fn returns 0 and fills *obj and
+ * grad[n] at w[n]; it is called once per distinct point.  w holds the start point and receives the result. */
+typedef int (*gpc_objective_fn)(void* user, const double* w, int n, double* obj, double* grad);
+int gpc_scg_minimise(gpc_objective_fn fn, void* user, double* w, int n, int max_iters, double param_tol, double obj_tol,
+                     double* trace, int* iters_out, int* evals_out);
 /* SVM-light files as CClctrl::readSvmlDataFile reads them (CClctrl.cpp:55-171): label first, then 1-based index:value
  * pairs separated by single spaces, '#' lines skipped, '\r' dropped; D = the largest index in the file.
  * gpc_svml_dims sizes the buffers; gpc_svml_read fills X (nrows x ncols, column-major, ld ldx, zero where absent) and y. */
