@@ -16,31 +16,70 @@ using namespace gpc;
 
 namespace {
 
-struct Scratch {  // RAII device scratch on one stream
+// Device scratch of one CMatrix-level call.  The stream and the buffers come from a per-thread cache (per device):
+// a level-0 / level-1 caller makes hundreds of small calls per optimiser iteration, and a
+// cudaStreamCreate + cudaMalloc/cudaFree round per call cost more than the work.  Buffers are handed out best-fit,
+// returned when the call ends, and the cache is dropped when it holds more than 4 GB of idle memory.
+struct ScratchCache {
+  struct Buf {
+    void* p;
+    size_t bytes;
+    bool busy;
+  };
   cudaStream_t s = nullptr;
-  std::vector<void*> ptrs;
+  std::vector<Buf> bufs;
+  ~ScratchCache() {}  // process exit: the driver reclaims everything; cudaFree here could run after the context died
+};
+static thread_local ScratchCache g_scratch[64];
+
+struct Scratch {  // RAII view of the cache for one call
+  cudaStream_t s = nullptr;
+  ScratchCache* cache = nullptr;
   int64_t launches = 0;
   int init(int device) {
     int ndev = 0;
     GPC_CUDA_CHECK(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) {
+    if (device < 0 || device >= ndev || device >= 64) {
       set_error("no such CUDA device");
       return GPC_ERR_CUDA;
     }
     GPC_CUDA_CHECK(cudaSetDevice(device));
-    GPC_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cache = &g_scratch[device];
+    if (!cache->s) GPC_CUDA_CHECK(cudaStreamCreateWithFlags(&cache->s, cudaStreamNonBlocking));
+    s = cache->s;
     return GPC_OK;
   }
   int alloc(double** p, size_t elems, bool zero) {
-    GPC_CUDA_CHECK(cudaMalloc(p, elems * sizeof(double)));
-    ptrs.push_back(*p);
+    const size_t need = (elems ? elems : 1) * sizeof(double);
+    int best = -1;
+    for (size_t i = 0; i < cache->bufs.size(); i++) {
+      const ScratchCache::Buf& b = cache->bufs[i];
+      if (!b.busy && b.bytes >= need && (best < 0 || b.bytes < cache->bufs[(size_t)best].bytes)) best = (int)i;
+    }
+    if (best >= 0 && cache->bufs[(size_t)best].bytes <= 4 * need + (1 << 20)) {
+      cache->bufs[(size_t)best].busy = true;
+      *p = (double*)cache->bufs[(size_t)best].p;
+    } else {
+      void* q = nullptr;
+      GPC_CUDA_CHECK(cudaMalloc(&q, need));
+      cache->bufs.push_back({q, need, true});
+      *p = (double*)q;
+    }
     if (zero) GPC_CUDA_CHECK(cudaMemsetAsync(*p, 0, elems * sizeof(double), s));
     return GPC_OK;
   }
   ~Scratch() {
+    if (!cache) return;
     if (s) cudaStreamSynchronize(s);
-    for (void* p : ptrs) cudaFree(p);
-    if (s) cudaStreamDestroy(s);
+    size_t idle = 0;
+    for (auto& b : cache->bufs) {
+      b.busy = false;
+      idle += b.bytes;
+    }
+    if (idle > ((size_t)4 << 30)) {
+      for (auto& b : cache->bufs) cudaFree(b.p);
+      cache->bufs.clear();
+    }
   }
 };
 
