@@ -98,27 +98,6 @@ __device__ __forceinline__ void oz_tc_fence_after() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void oz_tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]', int8 x int8 -> int32
-__device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1.
-__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-// instruction descriptor: D = S32 (2 @bit4), A = B = signed int8 (1 @bit7, 1 @bit10), both K-major, N>>3 @bit17, M>>4 @bit24
-__device__ __forceinline__ uint32_t oz_idesc(int n) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
-}
 __device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, int (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -283,7 +262,11 @@ __device__ __forceinline__ uint32_t oz_elect_one() {
       : "=r"(pred));
   return pred;
 }
-// descriptor = constant high word (SBO 1024 B, version 1, 128B swizzle) | low word (start address >> 4, LBO 1)
+// Shared-memory operand descriptor of a K-major tile with 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
+// (SBO), descriptor version 1.  Constant high word (SBO >> 4 @bit 32, version @bit 46, layout SWIZZLE_128B = 2 @bit 61)
+// | low word (start address >> 4, LBO field = 1).
+// Instruction descriptor: D = S32 (2 @bit 4), A = B = signed int8 (1 @bit 7, 1 @bit 10), both K-major, N >> 3 @bit 17,
+// M >> 4 @bit 24.
 constexpr uint32_t OZ_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t oz_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ void oz_mma_i8_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
@@ -311,8 +294,6 @@ __device__ __forceinline__ void oz_issue_slice(uint32_t tmem, uint32_t a_lo, uin
   for (int ks = 0; ks < OZ_BK / OZ_UK; ks++) {
 #pragma unroll
     for (int q0 = 0; q0 < S - P; q0 += 4) {
-      constexpr int dummy = 0;
-      (void)dummy;
       const int nq = (S - P - q0) < 4 ? (S - P - q0) : 4;
       const uint32_t acc = (P == 0 && ks == 0) ? first_acc : 1u;  // A slice 0 touches every level first
       oz_mma_i8_lo(tmem + (uint32_t)(P + q0) * OZ_BN, a_lo + ks * (OZ_UK >> 4), b_lo + q0 * (OZ_B_BYTES >> 4) + ks * (OZ_UK >> 4),
