@@ -476,7 +476,9 @@ int gpc_ctx_create(gpc_ctx** out, int device, int64_t Nmax, int Dmax, int dout_m
   if (!getenv("GPC_NO_FORK")) {
     c->fork = new Fork();
     c->fork->side.resize(8);
-    c->fork->ev.resize(512);
+    // two events per node of the recursions, N/128 - 1 nodes each: the round-robin pool must not wrap inside one
+    // evaluation (a re-recorded event would redirect a wait that has not been queued yet)
+    c->fork->ev.resize((size_t)(8 * (c->Npmax / TILE) + 512));
     for (auto& st : c->fork->side) GPC_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto& e : c->fork->ev) GPC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
