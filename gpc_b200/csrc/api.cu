@@ -228,7 +228,8 @@ static int winv_offdiag(const Dense& d, const double* A, int64_t lda, int64_t n1
   return gemm(d, gw);
 }
 
-int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, double* T, bool defer_top) {
+int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, double* T, bool defer_top,
+                  size_t tl_off) {
   // at the top level (defer_top) W21 waits for the inverse; its first factor T = L21 W11 is still started here on a
   // side stream when the caller announced that the inverse follows (d.top_t_ready): one full-GPU product that fills the
   // idle SMs of the latency-bound A22 recursion
@@ -237,10 +238,29 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
   if (n == TILE)
     return launch_potrf_leaf(A, lda, nullptr, d.info, (int)base, d.nvalid - base, d.logdet, d.s, d.launches, W, d.ldw);
   int64_t n1 = split(n), n2 = n - n1;
-  GPC_CHECK(potrf_inv_rec(d, A, lda, n1, base, T, false));
   double* A21 = A + n1;
   double* A22 = A + n1 + n1 * lda;
-  {  // L21 = A21 W11'   (W11'(kk, j) = W11(j, kk) is zero for kk > j: k ends at the tile's last column)
+  // L21 = A21 W11' cannot be formed in place.  With side streams the copy of A21 (final on entry: every earlier
+  // update is ordered before this point on the main stream) is taken NOW, concurrently with the A11 recursion, into
+  // this depth's slot of the copy pool; the product then reads the copy and writes A21 directly.
+  double* TL = d.TLpool ? d.TLpool + tl_off : nullptr;
+  cudaEvent_t e_copy = nullptr;
+  if (d.fk && TL) {
+    cudaEvent_t e0 = d.fk->event();
+    e_copy = d.fk->event();
+    cudaStream_t side = d.fk->copy_stream();
+    GPC_CUDA_CHECK(cudaEventRecord(e0, d.s));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(side, e0, 0));
+    GPC_CHECK(launch_copy_block(A21, lda, TL, n2, n2, n1, 1.0, side, d.launches));
+    GPC_CUDA_CHECK(cudaEventRecord(e_copy, side));
+  }
+  GPC_CHECK(potrf_inv_rec(d, A, lda, n1, base, T, false, tl_off + (size_t)n1 * n2));
+  if (e_copy) {  // W11'(kk, j) = W11(j, kk) is zero for kk > j: k ends at the tile's last column
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, e_copy, 0));
+    GemmCall g{TL, W, A21, n2, d.ldw, lda, n2, n1, n1, 1.0, 0.0, false, false, false};
+    g.b_tri = -1;
+    GPC_CHECK(gemm(d, g));
+  } else {
     GemmCall g{A21, W, d.tmpL, lda, d.ldw, n2, n2, n1, n1, 1.0, 0.0, false, false, false};
     g.b_tri = -1;
     GPC_CHECK(gemm(d, g));
@@ -265,7 +285,7 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
     GemmCall g{A21, A21, A22, lda, lda, lda, n2, n2, n1, -1.0, 1.0, false, false, true};
     GPC_CHECK(gemm(d, g));
   }
-  GPC_CHECK(potrf_inv_rec(d, A22, lda, n2, base + n1, T + (size_t)n1 * n2, false));
+  GPC_CHECK(potrf_inv_rec(d, A22, lda, n2, base + n1, T + (size_t)n1 * n2, false, tl_off + (size_t)n1 * n2));
   if (defer_top) {
     if (d.top_t_ready) *d.top_t_ready = t_done ? t_ready : nullptr;
     return GPC_OK;
@@ -350,6 +370,7 @@ static Dense dense_of(gpc_ctx* c) {
   // scratch inside the (not yet written) K^-1 buffer: tmpL then Tpool
   d.tmpL = c->Kinv;
   d.Tpool = c->Kinv ? c->Kinv + (size_t)(c->Npmax / 2 + TILE) * (size_t)(c->Npmax / 2 + TILE) : nullptr;
+  d.TLpool = d.Tpool ? d.Tpool + potrf_inv_tspace(c->Npmax) + 16 : nullptr;
   return d;
 }
 
@@ -357,7 +378,7 @@ static int ensure_inverse_buffers(gpc_ctx* c) {
   if (c->Kinv) return GPC_OK;
   size_t nn = (size_t)c->Npmax * c->Npmax;
   // K^-1 also serves as scratch of potrf_inv_rec: tmpL ((Np/2+TILE)^2) + Tpool (<= Np^2/3 + slack)
-  size_t scratch = (size_t)(c->Npmax / 2 + TILE) * (size_t)(c->Npmax / 2 + TILE) + potrf_inv_tspace(c->Npmax) + 16;
+  size_t scratch = (size_t)(c->Npmax / 2 + TILE) * (size_t)(c->Npmax / 2 + TILE) + 2 * (potrf_inv_tspace(c->Npmax) + 16);
   GPC_CUDA_CHECK(cudaMalloc(&c->Kinv, (nn > scratch ? nn : scratch) * sizeof(double)));
   if (c->use_winv) GPC_CUDA_CHECK(cudaMalloc(&c->Winv, nn * sizeof(double)));
   if (!c->use_winv) GPC_CUDA_CHECK(cudaMalloc(&c->W, (potri_workspace(c->Npmax) + 16) * sizeof(double)));
@@ -475,7 +496,7 @@ int gpc_ctx_create(gpc_ctx** out, int device, int64_t Nmax, int Dmax, int dout_m
   for (int i = 0; i < 6; i++) GPC_CUDA_CHECK(cudaEventCreate(&c->ev[i]));
   if (!getenv("GPC_NO_FORK")) {
     c->fork = new Fork();
-    c->fork->side.resize(8);
+    c->fork->side.resize(16);
     // two events per node of the recursions, N/128 - 1 nodes each: the round-robin pool must not wrap inside one
     // evaluation (a re-recorded event would redirect a wait that has not been queued yet)
     c->fork->ev.resize((size_t)(8 * (c->Npmax / TILE) + 512));
@@ -631,7 +652,7 @@ static int potrf_async(gpc_ctx* c) {
     // only where the factorisation is latency-bound (idle SMs to fill); at N = 32768 two concurrent large products
     // just contend for L2
     if (c->inverse_follows && c->Np <= 16384) d.top_t_ready = &c->top_t_ready;
-    return potrf_inv_rec(d, c->L, c->Np, c->Np, 0, d.Tpool, true);
+    return potrf_inv_rec(d, c->L, c->Np, c->Np, 0, d.Tpool, true, 0);
   }
   Dense d = dense_of(c);
   return potrf_rec(d, c->L, c->Np, c->Np, 0);

@@ -109,7 +109,11 @@ struct Fork {  // side streams + events for fork/join concurrency inside the rec
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> ev;
   size_t next_s = 0, next_e = 0;
-  cudaStream_t stream() { return side[next_s++ % side.size()]; }
+  // products rotate over all but the last four streams; those are kept for the short panel copies, which the main
+  // stream waits for and which must never queue behind a long product
+  cudaStream_t stream() { return side[next_s++ % (side.size() - 4)]; }
+  cudaStream_t copy_stream() { return side[side.size() - 4 + next_c++ % 4]; }
+  size_t next_c = 0;
   cudaEvent_t event() { return ev[next_e++ % ev.size()]; }
 };
 struct Dense {
@@ -127,6 +131,7 @@ struct Dense {
   int64_t ldw = 0;
   double* tmpL = nullptr;  // >= (n/2 + TILE) * (n/2) doubles: out-of-place result of a panel solve
   double* Tpool = nullptr; // >= tspace(n_total) doubles: T = L21 W11 per recursion depth
+  double* TLpool = nullptr; // >= tspace(n_total) doubles: copy of A21 per recursion depth (taken on a side stream)
   cudaEvent_t* top_t_ready = nullptr;  // where the event of an early top-level T product is left for inverse_from_W
   // inverse of the diagonal block of the factor at row/column dbase: the diagonal block of W when W is kept, else Dinv
   const double* dinv_blk(int64_t dbase, int64_t* ld) const {
@@ -141,7 +146,8 @@ struct Dense {
 size_t potrf_inv_tspace(int64_t n);  // doubles of Tpool needed for an n x n factorisation
 // in-place lower Cholesky of A (n x n block at row/column `base` of the matrix) AND W = L^-1 of the block into
 // d.Winv; defer_top: the top-level W21 (3/4 of the inverse's flops) is left to inverse_from_W
-int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, double* T, bool defer_top);
+int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t base, double* T, bool defer_top,
+                  size_t tl_off = 0);
 // completes W (if deferred) and forms Out = W' W = (L L')^-1, full symmetric
 int inverse_from_W(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, bool deferred_top);
 int trsm_rlt(const Dense& d, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n, int64_t dbase);
