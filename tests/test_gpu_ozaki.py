@@ -24,11 +24,12 @@ def _slices(R, K, kc, S, rng):
 
 
 @pytest.mark.parametrize("kc", [0, 1])
-@pytest.mark.parametrize("S", [8, 7, 3])
-def test_slicing_is_exact_to_the_last_digit(kc, S):
-    """x = 2^e_r * sum_p d_p 2^-(8p+6), d_0 in [-65, 65], d_p a balanced byte, remainder below half a unit of the last digit."""
+@pytest.mark.parametrize("S,R,K", [(8, 256, 384), (7, 256, 384), (3, 256, 384), (8, 1024, 512)])
+def test_slicing_is_exact_to_the_last_digit(kc, S, R, K):
+    """x = 2^e_r * sum_p d_p 2^-(8p+6), d_0 in [-65, 65], d_p a balanced byte, remainder below half a unit of the last digit.
+    Two shapes: few and many row blocks."""
     rng = np.random.default_rng(11 + S)
-    X, sl, sc = _slices(256, 384, kc, S, rng)
+    X, sl, sc = _slices(R, K, kc, S, rng)
     assert np.abs(sl[0].astype(int)).max() <= 65
     rec = np.zeros(X.shape, dtype=np.longdouble)
     for p in range(S):
