@@ -12,6 +12,13 @@ constexpr int TILE = 128;  // every device matrix is padded to a multiple of TIL
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 void set_error(const std::string& s);
+// the device current to the calling thread: function attributes (opt-in shared memory sizes) are per device, so the
+// "already configured" flags of the launch helpers are kept per device
+inline int cur_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
 // GPC_TRACE=1: synchronise after every kernel launch and log its name (bring-up / hang localisation)
 int trace_sync(const char* what, cudaStream_t s);
 #define GPC_CUDA_CHECK(expr)                                                                        \

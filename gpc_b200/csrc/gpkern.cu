@@ -267,15 +267,15 @@ __global__ void __launch_bounds__(KTHREADS, 2) kbuild_kernel(const __grid_consta
 
 int launch_kbuild(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, double* K, int64_t ldk,
                   cudaStream_t s, int64_t* launches) {
-  static bool configured = false;
+  static bool configured_dev[64] = {false};
   size_t smem = (size_t)2 * KT * ks.D * sizeof(double);
   if (smem > 200 * 1024) {
     set_error("kbuild: input dimension too large for the shared-memory stage");
     return GPC_ERR_ARG;
   }
-  if (!configured) {
+  if (!configured_dev[cur_device() & 63]) {
     GPC_CUDA_CHECK(cudaFuncSetAttribute(kbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    configured_dev[cur_device() & 63] = true;
   }
   int64_t nt = np / KT;
   int64_t tiles = nt * (nt + 1) / 2;
@@ -321,15 +321,15 @@ __global__ void __launch_bounds__(KTHREADS) kcross_kernel(const __grid_constant_
 int launch_kcross(const KSpec& ks, const double* X1, int64_t ldx1, int64_t n1, int64_t n1p, const double* X2,
                   int64_t ldx2, int64_t n2, int64_t n2p, double* Kc, int64_t ldk, cudaStream_t s, int64_t* launches,
                   int64_t col0) {
-  static bool configured = false;
+  static bool configured_dev[64] = {false};
   size_t smem = (size_t)2 * KT * ks.D * sizeof(double);
   if (smem > 200 * 1024) {
     set_error("kcross: input dimension too large for the shared-memory stage");
     return GPC_ERR_ARG;
   }
-  if (!configured) {
+  if (!configured_dev[cur_device() & 63]) {
     GPC_CUDA_CHECK(cudaFuncSetAttribute(kcross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    configured_dev[cur_device() & 63] = true;
   }
   dim3 grid((unsigned)(n1p / KT), (unsigned)(n2p / KT));
   kcross_kernel<<<grid, KTHREADS, smem, s>>>(ks, X1, ldx1, n1, X2, ldx2, n2, Kc, ldk, col0);
@@ -691,16 +691,16 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, const double* Cg, int64_t ldc,
                 const double* alpha, int64_t lda, int dout, int mode, double* partial, int max_ctas, double* g,
                 double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches, int64_t col0, int64_t ncols) {
-  static bool configured = false;
+  static bool configured_dev[64] = {false};
   if (mode != 0) dout = 0;
   size_t smem = (size_t)(4 * KT * ks.D + 2 * KT * (dout > 0 ? dout : 1) + NWARP * ks.nparams) * sizeof(double);
   if (smem > 200 * 1024) {
     set_error("grad: D / dout too large for the shared-memory stage");
     return GPC_ERR_ARG;
   }
-  if (!configured) {
+  if (!configured_dev[cur_device() & 63]) {
     GPC_CUDA_CHECK(cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    configured_dev[cur_device() & 63] = true;
   }
   int64_t nt = (n + KT - 1) / KT;
   int64_t tc0 = 0, tc1 = nt;

@@ -740,11 +740,11 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
     switch (S) {
 #define OZ_CASE(SS)                                                                                              \
   case SS: {                                                                                                     \
-    static bool configured = false;                                                                              \
+    static bool configured_dev[64] = {false};                                                                              \
     auto kern = oz_gemm_kernel<SS, oz_na(SS)>;                                                                   \
-    if (!configured) {                                                                                           \
+    if (!configured_dev[cur_device() & 63]) {                                                                                           \
       GPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem(SS))); \
-      configured = true;                                                                                         \
+      configured_dev[cur_device() & 63] = true;                                                                                         \
     }                                                                                                            \
     kern<<<(unsigned)ntiles, OZ_THREADS, oz_smem(SS), s>>>(tmA, tmB, a);                                         \
   } break;
