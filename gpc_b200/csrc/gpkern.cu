@@ -391,6 +391,9 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// WX: the GP-LVM's dL/dX is wanted; ND: some component needs x_i . x_j (lin, poly).  Compile-time so that the 4x4
+// register blocks they need (gdiff, gdot, dt: 96 registers) do not exist in the common hyper-parameter-only case.
+template <bool WX, bool ND>
 __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant__ KSpec ks, const double* __restrict__ X,
                                                        int64_t ldx, int64_t n, int64_t ntiles_edge, int64_t tc0,
                                                        int64_t tc1, const double* __restrict__ Cg, int64_t ldc,
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
     total = 0;
     for (int64_t c = tc0; c < tc1; c++) total += ntiles_edge - c;
   }
-  const bool wantX = gX != nullptr;
+  const bool wantX = WX && gX != nullptr;
 
   for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
     int bi, bj;
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
       }
 
     double r2[4][4], dt[4][4];
-    pair_r2_dot(si, sj, D, ti, tj, ks.need_r2, ks.need_dot, r2, dt);
+    pair_r2_dot(si, sj, D, ti, tj, ks.need_r2, ND && ks.need_dot, r2, dt);
     // coefficient of (x_j - x_i) resp. x_j in dL/dx_i, summed over components (GP-LVM)
     double gdiff[4][4], gdot[4][4];
 #pragma unroll
@@ -591,17 +594,20 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
             }
         } break;
         case GPC_KERN_LIN:
+          if (ND) {
 #pragma unroll
-          for (int a = 0; a < 4; a++)
+            for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-              g0 += c[a][b] * dt[a][b];
-              gdot[a][b] += c[a][b] * p[0];
-            }
+              for (int b = 0; b < 4; b++) {
+                g0 += c[a][b] * dt[a][b];
+                gdot[a][b] += c[a][b] * p[0];
+              }
+          }
           break;
         case GPC_KERN_POLY: {
           ng = 3;
           double deg = ks.degree[cmp];
+          if (ND)
 #pragma unroll
           for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -699,7 +705,10 @@ int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_
     return GPC_ERR_ARG;
   }
   if (!configured_dev[cur_device() & 63]) {
-    GPC_CUDA_CHECK(cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GPC_CUDA_CHECK(cudaFuncSetAttribute(grad_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GPC_CUDA_CHECK(cudaFuncSetAttribute(grad_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GPC_CUDA_CHECK(cudaFuncSetAttribute(grad_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GPC_CUDA_CHECK(cudaFuncSetAttribute(grad_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured_dev[cur_device() & 63] = true;
   }
   int64_t nt = (n + KT - 1) / KT;
@@ -714,8 +723,15 @@ int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_
   for (int64_t c = tc0; c < tc1; c++) total += nt - c;
   int ctas = (int)(total < max_ctas ? total : max_ctas);
   if (ctas < 1) ctas = 1;
-  grad_kernel<<<ctas, KTHREADS, smem, s>>>(ks, X, ldx, n, nt, tc0, tc1, Cg, ldc, alpha, lda, dout > 0 ? dout : 1, mode,
-                                           partial, gX, ldgx);
+  const bool wx = gX != nullptr, nd = ks.need_dot != 0;
+#define GPC_GRAD_LAUNCH(WX, ND)                                                                                       \
+  grad_kernel<WX, ND><<<ctas, KTHREADS, smem, s>>>(ks, X, ldx, n, nt, tc0, tc1, Cg, ldc, alpha, lda, dout > 0 ? dout : 1, \
+                                                   mode, partial, gX, ldgx)
+  if (wx && nd) GPC_GRAD_LAUNCH(true, true);
+  else if (wx) GPC_GRAD_LAUNCH(true, false);
+  else if (nd) GPC_GRAD_LAUNCH(false, true);
+  else GPC_GRAD_LAUNCH(false, false);
+#undef GPC_GRAD_LAUNCH
   if (launches) (*launches)++;
   GPC_CUDA_CHECK(cudaGetLastError());
   if (trace_sync("grad_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
