@@ -169,3 +169,42 @@ def test_engines_and_recursions_agree_on_a_full_evaluation():
     assert rel(ll1, ll0) < 1e-9 and rel(g1, g0) < 1e-8, (rel(ll1, ll0), rel(g1, g0))
     assert rel(ll2, ll0) < 1e-9 and rel(g2, g0) < 1e-8
     assert rel(mu1, mu0) < 1e-8 and rel(var1, var0) < 1e-8
+
+
+def test_posterior_after_factorisation_only_uses_block_substitution():
+    """gpc_potrf -> gpc_solve_alpha -> gpc_posterior without gpc_inverse: the top-level W21 is still deferred, so the
+    variance solve V = K* L^-T runs by block substitution with the diagonal halves of W (CGp::_posteriorVar,
+    CGp.cpp:600-613); the same call after gpc_inverse uses the single triangular product.  Both must agree with the
+    oracle."""
+    import ctypes as C
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(31)
+    N, D, Ns = 1500, 4, 300
+    X = rng.standard_normal((N, D))
+    y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((N, 1))
+    Xs = rng.standard_normal((Ns, D))
+    types = ["rbf", "white"]
+    tp = np.array([-0.7, 0.2, -2.0])
+    kern = G.make_kern(types, D, tp)
+    mu_ref, var_ref = O.gp_posterior(O.kern_from_trans(types, tp, D), X, y, Xs)
+    ctx = G.DeviceContext(N, D, 1)
+    try:
+        ctx.set_X(X)
+        ctx.set_M(y)
+        arr, n, keep = kern._kcomps()
+        L = lib()
+        check(L.gpc_kern_build(ctx.handle, arr, n))
+        info, logdet, quad = C.c_int(0), C.c_double(0), C.c_double(0)
+        assert check(L.gpc_potrf(ctx.handle, C.byref(info), C.byref(logdet))) == 0
+        check(L.gpc_solve_alpha(ctx.handle, C.byref(quad)))
+        Xf = np.asfortranarray(Xs)
+        for with_inverse in (False, True):
+            if with_inverse:
+                check(L.gpc_inverse(ctx.handle))
+            mu = np.zeros((Ns, 1), order="F")
+            var = np.zeros((Ns, 1), order="F")
+            check(L.gpc_posterior(ctx.handle, arr, n, ptr(Xf), Ns, Ns, ptr(mu), ptr(var)))
+            assert np.max(np.abs(mu - mu_ref) / np.maximum(1.0, np.abs(mu_ref))) < 1e-8, with_inverse
+            assert np.max(np.abs(var - var_ref) / np.maximum(1.0, np.abs(var_ref))) < 1e-8, with_inverse
+    finally:
+        ctx.close()
