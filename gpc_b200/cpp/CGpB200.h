@@ -1,0 +1,91 @@
+// CGpB200.h -- the reference's CGp with its exact-GP (FTC) hot path on the B200.
+//
+// A CGpB200 IS a CGp (CGp.h:9-482): same constructors, same public members (pX, py, X_u), same optimiser, stream and
+// display behaviour -- everything that is not the hot path is inherited, unmodified reference code.  The virtual entry
+// points the optimisers and front-ends drive,
+//     logLikelihood()               CGp.cpp:913-1013
+//     logLikelihoodGradient(g)      CGp.cpp:1016-1144   (updateG, updateCovGradient, CKern::getGradTransParams)
+//     out(yPred, X)                 CGp.cpp:445-452     (posteriorMeanVar CGp.cpp:535-663, then the noise model)
+// are re-bound to the C ABI of libgpc_b200.so (include/gpc_b200.h): K, LcholK, invK and Alpha live on the device in a
+// gpc_ctx owned by this object; one evaluation is ONE gpc_eval call (K build -> jitChol -> K^-1 -> alpha -> gradient,
+// one host synchronisation).  The non-virtual methods of the same path (posteriorMeanVar, posteriorMean, the two-output
+// out) are redeclared here so that code holding a CGpB200 uses the device too.
+//
+// Anything outside the device path -- sparse approximations (DTC/FITC/PITC), kernel components the library does not
+// implement, optimiseX on a CGp -- falls through to the inherited host implementation, call by call.
+//
+// No reference source is modified:  g++ -include gp_dropin.h gp.cpp  builds the reference's own `gp` front-end on this
+// class (oracle/build_ref.sh -> oracle/_ref/gp_l2), see INTEGRATION.md.
+#ifndef CGPB200_H
+#define CGPB200_H
+#include <vector>
+#include "CGp.h"
+#include "GpcKernBridge.h"
+#include "gpc_b200.h"
+
+class CGpB200 : public CGp
+{
+ public:
+  CGpB200();
+  CGpB200(CKern* kernel, CNoise* nois, CMatrix* Xin, int approxType = FTC, unsigned int actSetSize = 0, int verbos = 2);
+  CGpB200(unsigned int q, unsigned int d, CMatrix* Xin, CMatrix* yin, CKern* kernel, CNoise* nois, int approxType = FTC,
+          unsigned int actSetSize = 0, int verbos = 2);
+  virtual ~CGpB200();
+
+  // --- virtuals of CProbabilisticOptimisable / CGp / CMapModel
+  virtual double logLikelihood() const;
+  virtual double logLikelihoodGradient(CMatrix& g) const;
+  virtual void updateX();
+  virtual void out(CMatrix& yPred, const CMatrix& inData) const;
+  // --- non-virtual in CGp: same signatures, device-backed
+  void out(CMatrix& yPred, CMatrix& probPred, const CMatrix& inData) const;
+  void posteriorMeanVar(CMatrix& mu, CMatrix& varSigma, const CMatrix& X) const;
+  void posteriorMean(CMatrix& mu, const CMatrix& X) const;
+  // CGp::optimise (CGp.cpp:1537-1553).  With GPC_NATIVE_SCG=1 in the environment, the default SCG optimiser, no priors
+  // and fixed scales, the whole loop runs inside the library (gpc_gp_optimise_scg); otherwise the inherited optimisers
+  // drive the virtuals above.
+  void optimise(unsigned int iters = 1000);
+
+  // the host copies of the state (for -DDBG style inspection): N x N each, filled from the device on request
+  void downloadK(CMatrix& K) const { download(GPC_MAT_K, K, true); }
+  void downloadInvK(CMatrix& invK) const { download(GPC_MAT_KINV, invK, true); }
+  void downloadLcholK(CMatrix& L) const { download(GPC_MAT_L, L, true); }
+  void downloadAlpha(CMatrix& A) const { download(GPC_MAT_ALPHA, A, false); }
+  // which device the context is created on (default: $GPC_DEVICE or 0); call before the first evaluation
+  void setDevice(int dev);
+  // true when the next evaluation will run on the device (FTC, fixed X, every kernel component supported)
+  bool onDevice() const;
+  // drop the cached evaluation (call after changing *pX or *py in place without going through setOptParams/updateX)
+  void invalidate() const { state = STALE; }
+  // device evaluations so far (one per distinct parameter point)
+  unsigned long getNumDeviceEvals() const { return nEvals; }
+
+ private:
+  enum { STALE = 0, FACTORED = 1, EVALUATED = 2 };
+  void init();
+  bool sameInputs() const; // kernel parameters, scale, bias, data pointers unchanged since the cached evaluation
+  void snapshotInputs() const;
+  void upload() const;          // pX, (py - bias)/scale -> device (CGp::updateM, CGp.cpp:248-260)
+  void ensureEvaluated() const; // gpc_eval
+  void ensureFactored() const;  // K build + jitChol only (prediction does not need K^-1)
+  void download(int which, CMatrix& dst, bool square) const;
+  void fail(int rc) const;      // rc>0 -> MatrixNonPosDef, rc<0 -> Error(gpc_last_error())
+
+  mutable gpc_ctx* dev;
+  mutable int64_t devN;
+  mutable int devD, devd;
+  int device;
+  mutable GpcKernBridge bridge;
+  mutable int state;
+  mutable std::vector<double> key; // kernel natural parameters, scales, biases at the cached evaluation
+  mutable const CMatrix* keyX;
+  mutable const CMatrix* keyY;
+  mutable double evalOut[3]; // logdet, sum_j m_j' K^-1 m_j, jitter added
+  mutable std::vector<double> gNat;
+  mutable unsigned long nEvals;
+};
+
+// readGpFromFile (CGp.cpp:1701-1724) for this class
+CGpB200* readGpB200FromStream(istream& in);
+CGpB200* readGpB200FromFile(const string modelFileName, int verbosity = 2);
+#endif

@@ -68,4 +68,33 @@ if [ -f "$SHIMDIR/libgpc_lapack_shim.so" ]; then
       -Wl,-rpath,"$SP" -Wl,-rpath,'$ORIGIN/../../gpc_b200' -lm
   echo "build_ref: built $OUT/gp_b200, gplvm_b200 (reference objects + gpc_b200 Fortran shim)"
 fi
+# ---- level 2: the reference's UNMODIFIED front-ends compiled on the device-backed model classes of
+# gpc_b200/cpp (CGpB200 : CGp, CGplvmB200 : CGplvm) through a prefix header -- `-include gp_dropin.h` redirects the names
+# CGp / readGpFromFile inside gp.cpp only.  Every other object is the plain reference build of obj/ (host OpenBLAS for
+# whatever is not the hot path); the hot path goes through the C ABI of libgpc_b200.so.  Also the in-process comparison
+# driver of tests/cpp (reference class vs drop-in class on the same data).
+CPPDIR="$SHIMDIR/cpp"
+if [ -f "$SHIMDIR/libgpc_b200.so" ] && [ -d "$CPPDIR" ]; then
+  mkdir -p "$OUT/obj_l2"
+  CXXL="-std=gnu++98 -O3 -fPIC -w -D_LINUX -include $OUT/obj/blasmap.h -I$REF -I$HERE/../include -I$CPPDIR"
+  pids=()
+  for f in GpcKernBridge CGpB200 CGplvmB200; do
+    g++ $CXXL -c "$CPPDIR/$f.cpp" -o "$OUT/obj_l2/$f.o" &
+    pids+=($!)
+  done
+  g++ $CXXL -include "$CPPDIR/gp_dropin.h" -c "$REF/gp.cpp" -o "$OUT/obj_l2/gp.o" &
+  pids+=($!)
+  g++ $CXXL -include "$CPPDIR/gplvm_dropin.h" -c "$REF/gplvm.cpp" -o "$OUT/obj_l2/gplvm.o" &
+  pids+=($!)
+  g++ $CXXL -c "$HERE/../tests/cpp/cgp_b200_check.cpp" -o "$OUT/obj_l2/cgp_b200_check.o" &
+  pids+=($!)
+  for p in "${pids[@]}"; do wait "$p"; done
+  cd "$OUT/obj"
+  L2="../obj_l2/GpcKernBridge.o ../obj_l2/CGpB200.o ../obj_l2/CGplvmB200.o"
+  LNK="-L$SHIMDIR -lgpc_b200 $OB -Wl,-rpath,$SP -Wl,-rpath,\$ORIGIN/../../gpc_b200 -lm"
+  g++ -o "$OUT/gp_l2" ../obj_l2/gp.o $L2 CGp.o CGplvm.o $COMMON $LNK
+  g++ -o "$OUT/gplvm_l2" ../obj_l2/gplvm.o $L2 CGp.o CGplvm.o $COMMON $LNK
+  g++ -o "$OUT/cgp_b200_check" ../obj_l2/cgp_b200_check.o $L2 CGp.o CGplvm.o $COMMON $LNK
+  echo "build_ref: built $OUT/gp_l2, gplvm_l2, cgp_b200_check (reference front-ends on CGpB200 / CGplvmB200)"
+fi
 echo "build_ref: built $OUT/libgpcref.so, gp, gplvm (OpenBLAS: $OB)"

@@ -1,0 +1,122 @@
+"""The C++ host side of the drop-in on the B200 (north star: "host code stays C++ and calls through a thin C-ABI").
+
+gpc_b200/cpp/CGpB200 : CGp and CGplvmB200 : CGplvm re-bind the reference's virtual entry points (logLikelihood,
+logLikelihoodGradient, out) to libgpc_b200.so.  Two kinds of checks, both against the UNMODIFIED reference compiled by
+oracle/build_ref.sh:
+  * oracle/_ref/cgp_b200_check: reference class and drop-in class on the same data in ONE process -- log-likelihood,
+    optimiser-space gradient (priors, transforms, learnt scales), predictions through out(), and the point the
+    reference's own SCG optimiser reaches when it drives each class;
+  * oracle/_ref/gp_l2: the reference's gp.cpp front-end compiled with `-include gp_dropin.h` (no source change) next to
+    the plain OpenBLAS build: `gp learn` must print the same parameters and log-likelihood.
+Tolerance: 1e-8 relative (BASELINE.json north_star), looser only where an optimiser trajectory amplifies rounding."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+CHECK = os.path.join(REF, "cgp_b200_check")
+TOL = 1e-8
+
+
+def _check(*args):
+    if not os.path.exists(CHECK):
+        pytest.skip("oracle/_ref/cgp_b200_check not built (python __graft_entry__.py in the build container)")
+    out = subprocess.run([CHECK] + [str(a) for a in args], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if not l.startswith("Warning:")]
+    return json.loads("\n".join(lines))
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1.0)))
+
+
+def _assert_parity(r, opt_tol):
+    assert r["on_device"] == 1
+    assert r["evals_first"] == 1, "gradient + two likelihood calls at one point must cost ONE device evaluation"
+    assert _rel(r["ll_ref"], r["ll_dev"]) <= TOL
+    assert r["ll_dev"] == r["ll_dev_again"]
+    assert _rel(r["g_ref"], r["g_dev"]) <= TOL, (r["g_ref"], r["g_dev"])
+    assert _rel(r["out_ref"], r["out_dev"]) <= TOL
+    assert _rel(r["std_ref"], r["std_dev"]) <= TOL
+    if "out1_dev" in r:
+        assert r["out1_dev"] == r["out_dev"]
+    if "opt_ref" in r:
+        assert r["opt_ll_ref"] > r["ll_ref"]
+        assert _rel(r["opt_ref"], r["opt_dev"]) <= opt_tol, (r["opt_ref"], r["opt_dev"])
+        assert _rel(r["opt_ll_ref"], r["opt_ll_dev"]) <= opt_tol
+
+
+@pytest.mark.parametrize("N,D,d,kern,scale,prior,iters", [
+    (40, 1, 1, "rbf,bias,white", 0, 0, 15),          # the shape of config 1
+    (300, 3, 1, "rbf,lin,bias,white", 0, 0, 12),     # testGpftc's kernel
+    (260, 4, 2, "rbfard,bias,white", 0, 0, 12),      # two outputs
+    (220, 2, 1, "rbf,white", 1, 0, 12),              # learnt output scale (single output: the reference's limit)
+    (200, 3, 1, "matern52,poly,white", 0, 1, 12),    # a gamma prior on the first parameter
+    (500, 2, 3, "matern32,bias,white", 0, 1, 0),
+])
+def test_cgp_b200_matches_reference_cgp(N, D, d, kern, scale, prior, iters):
+    _assert_parity(_check("gp", N, D, d, 7, kern, scale, prior, iters), opt_tol=1e-5)
+
+
+@pytest.mark.parametrize("N,q,d,kern,scale,prior,iters", [
+    (120, 2, 5, "rbf,bias,white", 0, 0, 10),
+    (200, 3, 4, "rbfard,white", 1, 0, 0),
+    (150, 2, 6, "matern52,lin,white", 1, 1, 8),
+])
+def test_cgplvm_b200_matches_reference_cgplvm(N, q, d, kern, scale, prior, iters):
+    _assert_parity(_check("gplvm", N, q, d, 11, kern, scale, prior, iters), opt_tol=1e-4)
+
+
+def _write_svml(path, X, y):
+    with open(path, "w") as f:
+        for i in range(X.shape[0]):
+            f.write("%.17g %s\n" % (y[i], " ".join("%d:%.17g" % (j + 1, X[i, j]) for j in range(X.shape[1]))))
+
+
+def _learn(binary, data, model, iters, cwd):
+    out = subprocess.run([binary, "-v", "2", "learn", "-#", str(iters), data, model], cwd=cwd, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    vals = {}
+    for key in ("rbfinverseWidth", "rbfvariance", "biasvariance", "whitevariance", "Log likelihood"):
+        m = re.findall(re.escape(key) + r":\s*([-+0-9.eE]+)", out.stdout)
+        assert m, (key, out.stdout[-1500:])
+        vals[key] = float(m[-1])
+    return vals
+
+
+@pytest.mark.parametrize("case", ["config1", "n700"])
+def test_unmodified_gp_front_end_on_cgp_b200(tmp_path, case):
+    """`gp learn` (gp.cpp:331-431) built on CGpB200 by the prefix header: the kernel matrix, its factorisation, inverse
+    and gradients never exist on the host, the reference's SCG loop and model writer are untouched."""
+    gp_cpu, gp_l2 = os.path.join(REF, "gp"), os.path.join(REF, "gp_l2")
+    if not (os.path.exists(gp_cpu) and os.path.exists(gp_l2)):
+        pytest.skip("oracle/_ref/gp and gp_l2 not built")
+    if case == "config1":
+        f = np.load(os.path.join(HERE, "golden", "gp_reference.npz"))
+        X, y, iters = f["sinc_X"], np.asarray(f["sinc_y"]).ravel(), 100
+    else:
+        rng = np.random.default_rng(5)
+        X = rng.standard_normal((700, 3))
+        y = np.sin(X[:, 0]) * np.cos(0.5 * X[:, 1]) + 0.1 * rng.standard_normal(700)
+        iters = 10
+    data = str(tmp_path / "data.svml")
+    _write_svml(data, X, y)
+    a = _learn(gp_cpu, data, str(tmp_path / "m_cpu"), iters, str(tmp_path))
+    b = _learn(gp_l2, data, str(tmp_path / "m_l2"), iters, str(tmp_path))
+    for k in a:   # the CLI prints 6 significant digits
+        assert abs(a[k] - b[k]) <= 2e-5 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    if case == "config1":   # README.md:103-106 of the reference
+        assert abs(b["Log likelihood"] - 30.2364) < 1e-3
+    # the model file written by the drop-in build is read back by the plain reference build (gp display)
+    out = subprocess.run([gp_cpu, "display", str(tmp_path / "m_l2")], cwd=str(tmp_path), capture_output=True, text=True,
+                         timeout=120)
+    assert out.returncode == 0 and "rbfinverseWidth" in out.stdout
