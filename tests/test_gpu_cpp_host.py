@@ -120,3 +120,25 @@ def test_unmodified_gp_front_end_on_cgp_b200(tmp_path, case):
     out = subprocess.run([gp_cpu, "display", str(tmp_path / "m_l2")], cwd=str(tmp_path), capture_output=True, text=True,
                          timeout=120)
     assert out.returncode == 0 and "rbfinverseWidth" in out.stdout
+
+
+def test_unmodified_gplvm_front_end_on_cgplvm_b200_config5(tmp_path):
+    """BASELINE config 5 through the reference's own front-end: `gplvm -v 3 -s 1 learn -# 40 oilTrain.svml` (gplvm.cpp
+    compiled on CGplvmB200 by the prefix header; N=1000, q=2, rbf+bias+white, PCA initialisation and SCG are the
+    reference's code) against the objective log of the unmodified OpenBLAS build (printed with 6 digits)."""
+    exe = os.path.join(REF, "gplvm_l2")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gplvm_l2 not built")
+    Y = np.load(os.path.join(HERE, "golden", "oil_train.npz"))["Y"]
+    ref = json.load(open(os.path.join(HERE, "golden", "gplvm_c5_trajectory.json")))["objective"]
+    data = str(tmp_path / "oil.svml")
+    with open(data, "w") as f:
+        for i in range(Y.shape[0]):
+            f.write("0 " + " ".join("%d:%.17g" % (j + 1, Y[i, j]) for j in range(Y.shape[1])) + "\n")
+    out = subprocess.run([exe, "-v", "3", "-s", "1", "learn", "-#", "40", data, str(tmp_path / "oil.model")],
+                         cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    errs = [float(v) for _, v in re.findall(r"Iteration:\s*(\d+)\s*Error:\s*([-+0-9.eE]+)", out.stdout)]
+    assert len(errs) >= 40, out.stdout[-1500:]
+    for a, b in zip(errs[:40], ref[:40]):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (a, b)
