@@ -18,6 +18,14 @@ struct CGpNoiseTag
   friend type memberOf(CGpNoiseTag);
 };
 template struct PrivateMember<CGpNoiseTag, &CGp::pnoise>;
+// the scaled and biased targets m (CGp.h:364): kept by CGp::updateM under the reference's own MupToDate rules, which
+// the device path has to follow exactly (see upload())
+struct CGpMTag
+{
+  typedef CMatrix CGp::*type;
+  friend type memberOf(CGpMTag);
+};
+template struct PrivateMember<CGpMTag, &CGp::m>;
 
 int defaultDevice()
 {
@@ -90,14 +98,20 @@ bool CGpB200::sameInputs() const
   if(keyX != pX || keyY != py || !dev || devN != (int64_t)pX->getRows())
     return false;
   const std::vector<double>& p = bridge.naturalParams();
+  const CMatrix& mm = this->*memberOf(CGpMTag());
   unsigned int d = getOutputDim();
-  if(key.size() != p.size() + 2 * d)
+  size_t nm = (size_t)mm.getRows() * mm.getCols();
+  if(key.size() != p.size() + 2 * d + nm)
     return false;
   for(size_t i = 0; i < p.size(); i++)
     if(key[i] != p[i])
       return false;
   for(unsigned int j = 0; j < d; j++)
     if(key[p.size() + j] != getScaleVal(j) || key[p.size() + d + j] != getBiasVal(j))
+      return false;
+  const double* mv = mm.getVals();
+  for(size_t i = 0; i < nm; i++)
+    if(key[p.size() + 2 * d + i] != mv[i])
       return false;
   return true;
 }
@@ -108,6 +122,8 @@ void CGpB200::snapshotInputs() const
     key.push_back(getScaleVal(j));
   for(unsigned int j = 0; j < getOutputDim(); j++)
     key.push_back(getBiasVal(j));
+  const CMatrix& mm = this->*memberOf(CGpMTag());
+  key.insert(key.end(), mm.getVals(), mm.getVals() + (size_t)mm.getRows() * mm.getCols());
   keyX = pX;
   keyY = py;
 }
@@ -132,14 +148,16 @@ void CGpB200::upload() const
   int rc = gpc_set_X(dev, pX->getVals(), N, D, N);
   if(rc)
     fail(rc);
-  // m = (y - bias)/scale, CGp::updateM (CGp.cpp:248-260), formed on the device
-  std::vector<double> b(d), s(d);
-  for(int j = 0; j < d; j++)
-  {
-    b[j] = getBiasVal(j);
-    s[j] = getScaleVal(j);
-  }
-  rc = gpc_set_Y(dev, py->getVals(), N, d, N, &b[0], &s[0]);
+  // The targets are the reference's own m = (y - bias)/scale as CGp::updateM left it (CGp.cpp:248-260).  It is NOT
+  // recomputed from the current scale: when the output scale is learnt, CGp::setOptParams writes the new scale and calls
+  // updateM() while MupToDate is still true (CGp.cpp:429-437), so m keeps the scale it was last updated with -- the
+  // optimiser sees the scale only through the log term and its own gradient slot.  Same here, by construction.
+  const CMatrix& mm = this->*memberOf(CGpMTag());
+  DIMENSIONMATCH(mm.getRows() == (unsigned int)N && mm.getCols() == (unsigned int)d);
+  rc = gpc_set_M(dev, mm.getVals(), N, d, N);
+  if(rc)
+    fail(rc);
+  rc = gpc_ctx_sync(dev); // the caller may change m before the next call
   if(rc)
     fail(rc);
 }

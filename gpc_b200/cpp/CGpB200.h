@@ -63,9 +63,9 @@ class CGpB200 : public CGp
  private:
   enum { STALE = 0, FACTORED = 1, EVALUATED = 2 };
   void init();
-  bool sameInputs() const; // kernel parameters, scale, bias, data pointers unchanged since the cached evaluation
+  bool sameInputs() const; // kernel parameters, scale, bias, m, data pointers unchanged since the cached evaluation
   void snapshotInputs() const;
-  void upload() const;          // pX, (py - bias)/scale -> device (CGp::updateM, CGp.cpp:248-260)
+  void upload() const;          // *pX and the reference's m = (y - bias)/scale (CGp::updateM, CGp.cpp:248-260) -> device
   void ensureEvaluated() const; // gpc_eval
   void ensureFactored() const;  // K build + jitChol only (prediction does not need K^-1)
   void download(int which, CMatrix& dst, bool square) const;
@@ -77,7 +77,7 @@ class CGpB200 : public CGp
   int device;
   mutable GpcKernBridge bridge;
   mutable int state;
-  mutable std::vector<double> key; // kernel natural parameters, scales, biases at the cached evaluation
+  mutable std::vector<double> key; // kernel natural parameters, scales, biases, m at the cached evaluation
   mutable const CMatrix* keyX;
   mutable const CMatrix* keyY;
   mutable double evalOut[3]; // logdet, sum_j m_j' K^-1 m_j, jitter added

@@ -7,9 +7,13 @@
 //
 //   cgp_b200_check gp    N D d seed kern1,kern2,... [scale] [prior] [iters]
 //   cgp_b200_check gplvm N q d seed kern1,kern2,... [scale] [prior] [iters]
+//   cgp_b200_check bridge N D 0 seed kern1,kern2,... 0 [prior]   GpcKernBridge alone (host only)
+//   cgp_b200_check bench N D reps seed kern1,kern2,...      evaluations per second through CGpB200 alone (the metric of
+//                                                           bench.py, driven the way COptimisable drives a model)
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <ctime>
 #include <string>
 #include <vector>
 #include "CGpB200.h"
@@ -65,7 +69,9 @@ static void buildKernel(CCmpndKern& kern, const std::string& spec, unsigned int 
       k->addPrior(p, 0);
     }
     kern.addKern(k);
-    delete k;
+    // k is deliberately NOT deleted: the reference's ARD kernels copy their `scales` matrix with the compiler-generated
+    // CMatrix assignment (CKern.cpp:3178), so the clone inside `kern` shares k's buffer (gp.cpp keeps its component
+    // objects alive for the whole run for the same reason)
     pos = e + 1;
     c++;
   }
@@ -227,6 +233,105 @@ static int runGplvm(unsigned int N, unsigned int q, unsigned int d, const std::s
   return 0;
 }
 
+// GpcKernBridge on the host alone: the flattened component list, and finishGradient() against the reference's own
+// CKern::getGradTransParams (priors + transform factors) for a random symmetric covGrad
+static int runBridge(unsigned int N, unsigned int D, const std::string& spec, bool prior)
+{
+  CMatrix X(N, D);
+  for(unsigned int j = 0; j < D; j++)
+    for(unsigned int i = 0; i < N; i++)
+      X.setVal(normal01(), i, j);
+  CCmpndKern kern(X);
+  buildKernel(kern, spec, D, prior);
+  CMatrix covGrad(N, N);
+  for(unsigned int i = 0; i < N; i++)
+    for(unsigned int j = 0; j <= i; j++)
+    {
+      double v = normal01();
+      covGrad.setVal(v, i, j);
+      covGrad.setVal(v, j, i);
+    }
+  covGrad.setSymmetric(true);
+  CMatrix gTrans(1, kern.getNumParams()), gNat(1, kern.getNumParams());
+  kern.getGradTransParams(gTrans, X, covGrad, true); // the reference: priors + gradfact
+  kern.getGradParams(gNat, X, covGrad, false);       // natural gradient, no priors: what the device returns
+  GpcKernBridge bridge;
+  bool ok = bridge.sync(&kern, D);
+  printf("{\"mode\": \"bridge\", \"supported\": %d, \"ncomp\": %d, \"nparams\": %u,\n", ok ? 1 : 0, ok ? bridge.numComps() : 0,
+         ok ? bridge.getNumParams() : 0);
+  if(ok)
+  {
+    printf("\"types\": [");
+    for(int i = 0; i < bridge.numComps(); i++)
+      printf("%s%d", i ? ", " : "", bridge.comps()[i].type);
+    printf("],\n\"params\": [");
+    for(unsigned int i = 0; i < bridge.getNumParams(); i++)
+      printf("%s%.17g", i ? ", " : "", bridge.naturalParams()[i]);
+    printf("],\n\"kern_params\": [");
+    for(unsigned int i = 0; i < kern.getNumParams(); i++)
+      printf("%s%.17g", i ? ", " : "", kern.getParam(i));
+    printf("],\n");
+    std::vector<double> g(gNat.getVals(), gNat.getVals() + kern.getNumParams());
+    bridge.finishGradient(&kern, &g[0]);
+    CMatrix gBridge(1, kern.getNumParams());
+    for(unsigned int i = 0; i < kern.getNumParams(); i++)
+      gBridge.setVal(g[i], i);
+    printVec("g_bridge", gBridge);
+  }
+  printVec("g_ref", gTrans, true);
+  printf("}\n");
+  return 0;
+}
+
+// setOptParams(theta) -> logLikelihoodGradient(g): one evaluation as SURVEY 8(d) M1 defines it, through the C++ class
+static int runBench(unsigned int N, unsigned int D, int reps, const std::string& spec)
+{
+  CMatrix X(N, D), y(N, 1);
+  for(unsigned int j = 0; j < D; j++)
+    for(unsigned int i = 0; i < N; i++)
+      X.setVal(normal01(), i, j);
+  double mean = 0.0;
+  for(unsigned int i = 0; i < N; i++)
+  {
+    y.setVal(sin(X.getVal(i, 0)) + 0.1 * normal01(), i, 0);
+    mean += y.getVal(i, 0) / N;
+  }
+  CCmpndKern kern(X);
+  buildKernel(kern, spec, D, false);
+  for(unsigned int i = 0; i < kern.getNumParams(); i++) // gamma = 1/D, variance 1, white 0.01: SURVEY 8(d) C2
+  {
+    std::string nm = kern.getParamName(i);
+    double v = 1.0;
+    if(nm.find("white") == 0)
+      v = 0.01;
+    else if(nm.find("inverseWidth") != std::string::npos)
+      v = 1.0 / D;
+    kern.setParam(v, i);
+  }
+  CGaussianNoise noise(&y);
+  CGpB200 dev(&kern, &noise, &X, CGp::FTC, 0, 0);
+  dev.setBiasVal(mean, 0);
+  dev.updateM();
+  CMatrix theta(1, dev.getOptNumParams()), g(1, dev.getOptNumParams());
+  dev.getOptParams(theta);
+  double ll = 0.0;
+  struct timespec t0, t1;
+  for(int r = -3; r < reps; r++)
+  {
+    if(r == 0)
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+    theta.setVal(theta.getVal(0) + 1e-9, 0); // a new point every step: nothing is served from the cache
+    dev.setOptParams(theta);
+    ll = dev.logLikelihoodGradient(g);
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  double sec = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+  printf("{\"mode\": \"bench\", \"N\": %u, \"D\": %u, \"reps\": %d, \"ms_per_eval\": %.4f, \"evals_per_sec\": %.3f, "
+         "\"ll\": %.12g, \"device_evals\": %lu}\n",
+         N, D, reps, 1e3 * sec / reps, reps / sec, ll, dev.getNumDeviceEvals());
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
   if(argc < 7)
@@ -249,6 +354,10 @@ int main(int argc, char** argv)
       return runGp(N, D, d, spec, scale, prior, iters);
     if(mode == "gplvm")
       return runGplvm(N, D, d, spec, scale, prior, iters);
+    if(mode == "bridge")
+      return runBridge(N, D, spec, prior);
+    if(mode == "bench")
+      return runBench(N, D, (int)d, spec);
   }
   catch(ndlexceptions::Error& e)
   {

@@ -49,3 +49,51 @@ def test_device_path_fails_loudly_without_a_gpu():
     out = _run("gp", 40, 2, 1, 3, "rbf,bias,white", 0, 0, 0, expect_ok=False)
     assert out.returncode == 1
     assert "gpc_b200:" in out.stderr
+
+
+def _sinc_svml(path):
+    import numpy as np
+    f = np.load(os.path.join(HERE, "golden", "gp_reference.npz"))
+    X, y = f["sinc_X"], np.asarray(f["sinc_y"]).ravel()
+    with open(path, "w") as fh:
+        for i in range(len(y)):
+            fh.write("%.17g 1:%.17g\n" % (y[i], X[i, 0]))
+
+
+def test_unmodified_front_end_on_the_drop_in_class_learn_and_gnuplot(tmp_path):
+    """The reference's gp.cpp compiled with `-include gp_dropin.h` (oracle/_ref/gp_l2) next to the plain build: `gp learn`
+    with a kernel outside the device path writes the same model file, and `gp gnuplot` on the model it reads back
+    (readGpB200FromFile -> CGpB200() -> fromStream, then out() through the private noise pointer) writes the same
+    plot data -- the whole front-end flow, constructors, stream I/O and the virtual dispatch, on any machine."""
+    gp, gp_l2 = (os.path.join(ROOT, "oracle", "_ref", n) for n in ("gp", "gp_l2"))
+    if not (os.path.exists(gp) and os.path.exists(gp_l2)):
+        pytest.skip("oracle/_ref/gp, gp_l2 not built")
+    _sinc_svml(str(tmp_path / "sinc.svml"))
+    for exe, tag in ((gp, "ref"), (gp_l2, "l2")):
+        out = subprocess.run([exe, "-v", "1", "-s", "7", "learn", "-k", "ratquad", "-#", "30", "sinc.svml", "m_" + tag],
+                             cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+        out = subprocess.run([exe, "gnuplot", "sinc.svml", "m_" + tag, "plot_" + tag], cwd=str(tmp_path),
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    body = lambda p: open(str(tmp_path / p)).read().split("\n", 1)[1]   # line 1 records the command line
+    assert body("m_ref") == body("m_l2")
+    for part in ("line_data", "error_bar_data", "scatter_data"):
+        assert open(str(tmp_path / ("plot_ref_%s.dat" % part))).read() == \
+            open(str(tmp_path / ("plot_l2_%s.dat" % part))).read(), part
+
+
+@pytest.mark.parametrize("spec,D,prior", [("rbf,bias,white", 1, 0), ("rbfard,matern52,lin,poly,bias,white", 3, 1),
+                                          ("matern32,rbf,white", 2, 1)])
+def test_kernel_bridge_flattening_and_gradient_finish(spec, D, prior):
+    """GpcKernBridge on the host: component types / natural parameters in the reference's order, and finishGradient()
+    (each component's prior gradient, then the transform factor) reproduces CKern::getGradTransParams (CKern.cpp:50-63)
+    from the natural, prior-free gradient -- which is what the device returns."""
+    import numpy as np
+    r = _run("bridge", 30, D, 0, 5, spec, 0, prior)
+    code = {"white": 0, "bias": 1, "rbf": 2, "rbfard": 3, "matern32": 4, "matern52": 5, "lin": 6, "poly": 7}
+    assert r["supported"] == 1
+    assert r["types"] == [code[k] for k in spec.split(",")]
+    assert r["params"] == r["kern_params"] and len(r["params"]) == r["nparams"]
+    a, b = np.array(r["g_bridge"]), np.array(r["g_ref"])
+    assert np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))) < 1e-14

@@ -142,3 +142,25 @@ def test_unmodified_gplvm_front_end_on_cgplvm_b200_config5(tmp_path):
     assert len(errs) >= 40, out.stdout[-1500:]
     for a, b in zip(errs[:40], ref[:40]):
         assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (a, b)
+
+
+def test_unmodified_gp_front_end_gnuplot_on_cgp_b200(tmp_path):
+    """`gp gnuplot` (gp.cpp:567-906: the model file is read back into a default-constructed CGpB200, the prediction
+    grid goes through out() -> gpc_kern_build, gpc_jitchol, gpc_posterior): plot data against the OpenBLAS build."""
+    gp_cpu, gp_l2 = os.path.join(REF, "gp"), os.path.join(REF, "gp_l2")
+    if not (os.path.exists(gp_cpu) and os.path.exists(gp_l2)):
+        pytest.skip("oracle/_ref/gp and gp_l2 not built")
+    f = np.load(os.path.join(HERE, "golden", "gp_reference.npz"))
+    _write_svml(str(tmp_path / "sinc.svml"), f["sinc_X"], np.asarray(f["sinc_y"]).ravel())
+    out = subprocess.run([gp_cpu, "-v", "1", "learn", "-#", "60", "sinc.svml", "model"], cwd=str(tmp_path),
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    for exe, tag in ((gp_cpu, "ref"), (gp_l2, "l2")):   # the SAME model file through both builds
+        out = subprocess.run([exe, "gnuplot", "sinc.svml", "model", "plot_" + tag], cwd=str(tmp_path),
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    for part, tol in (("line_data", 2e-5), ("error_bar_data", 1e-8)):   # 6 and 18 printed digits
+        a = np.loadtxt(str(tmp_path / ("plot_ref_%s.dat" % part)))
+        b = np.loadtxt(str(tmp_path / ("plot_l2_%s.dat" % part)))
+        assert a.shape == b.shape and a.size > 0
+        assert _rel(a, b) <= tol, part
