@@ -3,7 +3,7 @@
 # Compiles the UNMODIFIED reference (SheffieldML/GPc) from the sources WHERE THEY LIE under
 # $GPC_REFERENCE (default /root/reference) into oracle/_ref/ (git-ignored, travels with gpurun):
 #   oracle/_ref/libgpcref.so   reference objects + oracle/ref_driver.cpp (ctypes facade)
-#   oracle/_ref/gp, gplvm      the reference CLI front-ends (for end-to-end trajectories)
+#   oracle/_ref/gp, gplvm, ivm the reference CLI front-ends (for end-to-end trajectories)
 # No reference source is copied into this repository.  The reference's own build system is not used
 # (it wants gfortran + system BLAS): three shims instead:
 #   1. -std=gnu++98 (dynamic exception specs, ostream->void*)
@@ -26,7 +26,7 @@ for s in dsyev dsysv dgetrf dgetri dpotrf dpotri dswap dcopy dscal daxpy ddot dn
   echo "#define ${s}_ scipy_${s}_"
 done > "$OUT/obj/blasmap.h"
 CXXF="-std=gnu++98 -O3 -fPIC -w -D_LINUX -include $OUT/obj/blasmap.h -I$REF"
-SRCS="CClctrl CGp CGplvm CMatrix CNoise ndlutil ndlstrutil CTransform COptimisable CKern CDist ndlassert gp gplvm"
+SRCS="CClctrl CGp CGplvm CIvm CMatrix CNoise ndlutil ndlstrutil CTransform COptimisable CKern CDist ndlassert gp gplvm ivm"
 pids=()
 for f in $SRCS; do
   if [ ! -f "$OUT/obj/$f.o" ] || [ "$REF/$f.cpp" -nt "$OUT/obj/$f.o" ]; then
@@ -43,6 +43,7 @@ COMMON="CClctrl.o CMatrix.o ndlfortran.o lbfgs_stub.o CNoise.o ndlutil.o ndlstru
 g++ -shared -o "$OUT/libgpcref.so" ref_driver.o CGp.o CGplvm.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
 g++ -o "$OUT/gp" gp.o CGp.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
 g++ -o "$OUT/gplvm" gplvm.o CGplvm.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
+g++ -o "$OUT/ivm" ivm.o CIvm.o $COMMON "$OB" -Wl,-rpath,"$SP" -lm
 # ---- the UNMODIFIED reference with its five hot BLAS/LAPACK calls resolved by the B200 library (seam (1)):
 # same sources, same flags, but dpotrf_/dpotri_/dtrsm_/dsyrk_/dgemm_ keep their plain Fortran names and are taken from
 # gpc_b200/libgpc_lapack_shim.so; everything else still comes from OpenBLAS.  Built only when the shim exists.
@@ -52,7 +53,7 @@ if [ -f "$SHIMDIR/libgpc_lapack_shim.so" ]; then
   grep -v -E "define (dpotrf|dpotri|dtrsm|dsyrk|dgemm)_ " "$OUT/obj/blasmap.h" > "$OUT/obj_b200/blasmap.h"
   CXXB="-std=gnu++98 -O3 -fPIC -w -D_LINUX -include $OUT/obj_b200/blasmap.h -I$REF"
   pids=()
-  for f in CClctrl CGp CGplvm CMatrix CNoise ndlutil ndlstrutil CTransform COptimisable CKern CDist ndlassert gp gplvm; do
+  for f in CClctrl CGp CGplvm CIvm CMatrix CNoise ndlutil ndlstrutil CTransform COptimisable CKern CDist ndlassert gp gplvm ivm; do
     if [ ! -f "$OUT/obj_b200/$f.o" ] || [ "$REF/$f.cpp" -nt "$OUT/obj_b200/$f.o" ]; then
       g++ $CXXB -c "$REF/$f.cpp" -o "$OUT/obj_b200/$f.o" &
       pids+=($!)
@@ -66,7 +67,10 @@ if [ -f "$SHIMDIR/libgpc_lapack_shim.so" ]; then
   g++ -o "$OUT/gplvm_b200" gplvm.o CGplvm.o CClctrl.o CMatrix.o ../obj/ndlfortran.o ../obj/lbfgs_stub.o CNoise.o ndlutil.o ndlstrutil.o \
       CTransform.o COptimisable.o CKern.o CDist.o ndlassert.o -L"$SHIMDIR" -lgpc_lapack_shim -lgpc_b200 "$OB" \
       -Wl,-rpath,"$SP" -Wl,-rpath,'$ORIGIN/../../gpc_b200' -lm
-  echo "build_ref: built $OUT/gp_b200, gplvm_b200 (reference objects + gpc_b200 Fortran shim)"
+  g++ -o "$OUT/ivm_b200" ivm.o CIvm.o CClctrl.o CMatrix.o ../obj/ndlfortran.o ../obj/lbfgs_stub.o CNoise.o ndlutil.o ndlstrutil.o \
+      CTransform.o COptimisable.o CKern.o CDist.o ndlassert.o -L"$SHIMDIR" -lgpc_lapack_shim -lgpc_b200 "$OB" \
+      -Wl,-rpath,"$SP" -Wl,-rpath,'$ORIGIN/../../gpc_b200' -lm
+  echo "build_ref: built $OUT/gp_b200, gplvm_b200, ivm_b200 (reference objects + gpc_b200 Fortran shim)"
 fi
 # ---- level 2: the reference's UNMODIFIED front-ends compiled on the device-backed model classes of
 # gpc_b200/cpp (CGpB200 : CGp, CGplvmB200 : CGplvm) through a prefix header -- `-include gp_dropin.h` redirects the names

@@ -162,11 +162,19 @@ def random_cases():
     np.savez_compressed(os.path.join(HERE, "random_reference.npz"), **out)
 
 
+def ivm_fixture():
+    """examples/unitsquaregp.svml (500 x 2, labels +-1): the data of the reference's IVM walk-through
+    (README.md:234, `ivm learn -a 200 -k rbf examples/unitsquaregp.svml`), for tests/test_gpu_shim.py."""
+    X, y = load_svml(EX + "unitsquaregp.svml")
+    np.savez_compressed(os.path.join(HERE, "unitsquaregp.npz"), X=X, y=y)
+
+
 if __name__ == "__main__":
     kern_fixtures()
     matrix_fixtures()
     gp_fixtures()
     random_cases()
+    ivm_fixture()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
