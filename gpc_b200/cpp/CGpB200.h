@@ -15,7 +15,7 @@
 // implement, optimiseX on a CGp -- falls through to the inherited host implementation, call by call.
 //
 // No reference source is modified:  g++ -include gp_dropin.h gp.cpp  builds the reference's own `gp` front-end on this
-// class (oracle/build_ref.sh -> oracle/_ref/gp_l2), see INTEGRATION.md.
+// class (build recipe and the resulting gp_l2 / gplvm_l2 executables: INTEGRATION.md, level 2).
 #ifndef CGPB200_H
 #define CGPB200_H
 #include <vector>
