@@ -97,3 +97,23 @@ def test_kernel_bridge_flattening_and_gradient_finish(spec, D, prior):
     assert r["params"] == r["kern_params"] and len(r["params"]) == r["nparams"]
     a, b = np.array(r["g_bridge"]), np.array(r["g_ref"])
     assert np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))) < 1e-14
+
+
+def test_unmodified_gplvm_front_end_on_the_drop_in_class_falls_through(tmp_path):
+    """gplvm.cpp compiled with `-include gplvm_dropin.h` (oracle/_ref/gplvm_l2): with the mlp kernel (not a device
+    kernel) `gplvm learn` must write the same model as the plain build -- constructors, PCA initialisation, the
+    optimiser's virtual dispatch and the stream writer all go through CGplvmB200."""
+    import numpy as np
+    a, b = (os.path.join(ROOT, "oracle", "_ref", n) for n in ("gplvm", "gplvm_l2"))
+    if not (os.path.exists(a) and os.path.exists(b)):
+        pytest.skip("oracle/_ref/gplvm, gplvm_l2 not built")
+    Y = np.load(os.path.join(HERE, "golden", "oil_train.npz"))["Y"][:100]
+    with open(str(tmp_path / "oil100.svml"), "w") as f:
+        for i in range(Y.shape[0]):
+            f.write("0 " + " ".join("%d:%.17g" % (j + 1, Y[i, j]) for j in range(Y.shape[1])) + "\n")
+    for exe, tag in ((a, "ref"), (b, "l2")):
+        out = subprocess.run([exe, "-v", "1", "-s", "1", "learn", "-k", "mlp", "-#", "15", "oil100.svml", "m_" + tag],
+                             cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    body = lambda p: open(str(tmp_path / p)).read().split("\n", 1)[1]
+    assert body("m_ref") == body("m_l2")
