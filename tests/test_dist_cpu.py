@@ -132,7 +132,8 @@ def _worker(rank, world, port, N, D, NB, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,N,NB", [(1, 200, 128), (2, 300, 128), (2, 700, 256)])
+@pytest.mark.parametrize("world,N,NB", [(1, 200, 128), (2, 300, 128), (2, 700, 256), (4, 900, 128), (8, 1100, 128),
+                                         (8, 300, 128)])   # the last: more ranks than block columns
 def test_distributed_schedule_matches_oracle(tmp_path, world, N, NB):
     from oracle import gp_oracle as O
     D = 3
