@@ -36,6 +36,19 @@ class CGp:
         self._out = np.zeros(3)
         self._g = None
 
+    @classmethod
+    def fromModelFile(cls, path, X, y, device=0):
+        """readGpFromFile + the caller's data, as gp.cpp:486-490 / 562-622 do for relearn, display and gnuplot: the
+        file's kernel, scale and bias (native reader, gpc_gp_model_read) around X and y."""
+        from . import io
+        m = io.read_gp_model(path)
+        return cls(io.kern_from_model(m), X, y, bias=m["bias"], scale=m["scale"], device=device)
+
+    def writeModelFile(self, path, comment=""):
+        """writeGpToFile (CGp.cpp:1689-1692): a model file the reference's gp display / gnuplot / relearn read."""
+        from . import io
+        io.write_gp_model(path, io.model_from_gp(self), comment)
+
     # --- CGp::updateM (CGp.cpp:248-260)
     def updateM(self):
         self.m = fmat((self.y - self.bias[None, :]) / self.scale[None, :])

@@ -235,6 +235,38 @@ int gpc_scg_minimise(gpc_objective_fn fn, void* user, double* w, int n, int max_
 int gpc_svml_dims(const char* path, int64_t* nrows, int* ncols);
 int gpc_svml_read(const char* path, double* X, int64_t ldx, double* y, int64_t nrows, int ncols);
 
+/* GP model files: the text format `gp learn` writes and `gp display / gnuplot / relearn` read (CGp::writeParamsToStream /
+ * readParamsFromStream CGp.cpp:1605-1682; CStreamInterface CNdlInterfaces.h:21-175; CMatrix CMatrix.cpp:1057-1097,
+ * 1158-1172; CKern CKern.cpp:15-26, 94-126, 2668-2705, 4192-4278; CNoise CNoise.cpp:275-305, 1813-1836).  Exact FTC models
+ * with the device kernels; X and y are not part of the file (gp.cpp:486-490 reloads them).  Files written here are
+ * byte-identical to the reference's for the same model (after the "# comment" line) and files are read the way the
+ * reference reads them, quirks included: nested versions and matrix entries are hexfloat text, integer values are written
+ * as integers, and an entry WITHOUT a '.' is read with atoi (CMatrix.cpp:1081-1085) -- 0.25, written "0x1p-2", comes back
+ * as 0.  gpc_gp_model_check_roundtrip counts the values of a model that would be lost that way (*first_lost = the first).
+ * A file with priors is rejected, as the reference's own reader rejects it (CDist.cpp:4-10 vs 338-357). */
+#define GPC_MODEL_MAX_OUT 256
+typedef struct gpc_gp_model {
+  int64_t num_data;
+  int input_dim, output_dim;
+  int approx_type;         /* CGp::FTC = 0 (field "sparseApproximation"); anything else is rejected */
+  unsigned int num_active; /* written as is (the CLI leaves 0 or 4294967295 for FTC) */
+  int learn_scale, learn_bias;
+  int top_is_cmpnd;        /* 1: CCmpndKern of ncomp components; 0: a single kernel object (ncomp = 1) */
+  int kern_input_dim;
+  int ncomp;
+  int type[GPC_MAX_COMPONENTS];    /* gpc_kern_type */
+  int nparams[GPC_MAX_COMPONENTS];
+  double degree[GPC_MAX_COMPONENTS]; /* POLY only */
+  double kern_params[GPC_MAX_PARAMS]; /* NATURAL values, component order (CKern::getParams) */
+  double scale[GPC_MODEL_MAX_OUT], bias[GPC_MODEL_MAX_OUT];
+  char noise_type[16];     /* "gaussian" for gp learn (CNoise.cpp:1821-1833) */
+  int noise_output_dim, noise_nparams;
+  double noise_params[GPC_MODEL_MAX_OUT + 8]; /* gaussian: bias_1..bias_d, sigma2 */
+} gpc_gp_model;
+int gpc_gp_model_read(const char* path, gpc_gp_model* out);
+int gpc_gp_model_write(const char* path, const gpc_gp_model* model, const char* comment);
+int gpc_gp_model_check_roundtrip(const gpc_gp_model* model, int* nlost, double* first_lost);
+
 /* ---- fp64 GEMM engine selection -------------------------------------------------------------------- */
 /* The dsyrk_/dgemm_ work below dpotrf_/dpotri_ (lapack.h:59-73) runs on one of two engines:
  *   DMMA  : mma.sync.m8n8k4.f64 (the fp64 tensor pipe, 37 TFLOP/s peak);

@@ -8,6 +8,8 @@
 //   cgp_b200_check gp    N D d seed kern1,kern2,... [scale] [prior] [iters]
 //   cgp_b200_check gplvm N q d seed kern1,kern2,... [scale] [prior] [iters]
 //   cgp_b200_check bridge N D 0 seed kern1,kern2,... 0 [prior]   GpcKernBridge alone (host only)
+//   cgp_b200_check modelwrite N D d seed kern1,kern2,... scale prior path   the REFERENCE writes a gp model file (CGp.cpp:1640-1666)
+//   cgp_b200_check modelread 0 0 0 0 path                                   the REFERENCE reads one and prints what it holds
 //   cgp_b200_check bench N D reps seed kern1,kern2,...      evaluations per second through CGpB200 alone (the metric of
 //                                                           bench.py, driven the way COptimisable drives a model)
 #include <cstdio>
@@ -50,6 +52,12 @@ static CKern* makeComponent(const std::string& name, unsigned int D)
   exit(2);
 }
 
+// CComponentKern::components is protected (CKern.h:469-472): member pointer formed inside a derived class
+struct DriverComponentPeek : public CComponentKern
+{
+  static std::vector<CKern*> CComponentKern::*member() { return &DriverComponentPeek::components; }
+};
+
 // the same compound kernel twice (one per model), parameters set to a deterministic non-default point
 static void buildKernel(CCmpndKern& kern, const std::string& spec, unsigned int D, bool prior)
 {
@@ -61,14 +69,17 @@ static void buildKernel(CCmpndKern& kern, const std::string& spec, unsigned int 
     if(e == std::string::npos)
       e = spec.size();
     CKern* k = makeComponent(spec.substr(pos, e - pos), D);
+    kern.addKern(k);
     if(prior && c == 0)
     {
-      CDist* p = new CGammaDist(); // a prior on the first parameter of the first component
+      // a gamma prior on the first parameter of the first component.  It goes onto the CLONE the compound kernel holds:
+      // CKern's copy constructor does not carry priors over, so one added before addKern would be lost
+      CKern* held = (static_cast<CComponentKern&>(kern).*DriverComponentPeek::member())[0];
+      CDist* p = new CGammaDist();
       p->setParam(1.5, 0);
       p->setParam(0.7, 1);
-      k->addPrior(p, 0);
+      held->addPrior(p, 0);
     }
-    kern.addKern(k);
     // k is deliberately NOT deleted: the reference's ARD kernels copy their `scales` matrix with the compiler-generated
     // CMatrix assignment (CKern.cpp:3178), so the clone inside `kern` shares k's buffer (gp.cpp keeps its component
     // objects alive for the whole run for the same reason)
@@ -283,6 +294,108 @@ static int runBridge(unsigned int N, unsigned int D, const std::string& spec, bo
   return 0;
 }
 
+// ---- model files: the reference as the oracle of gpc_gp_model_read / gpc_gp_model_write (tests/test_model_io_cpu.py)
+namespace
+{
+template <typename Tag, typename Tag::type Member> struct DriverPrivateMember
+{
+  friend typename Tag::type driverMemberOf(Tag) { return Member; }
+};
+struct DriverNoiseTag
+{
+  typedef CNoise* CGp::*type;
+  friend type driverMemberOf(DriverNoiseTag);
+};
+template struct DriverPrivateMember<DriverNoiseTag, &CGp::pnoise>;
+} // namespace
+
+static void dumpModel(const CGp& model)
+{
+  printf("{\"num_data\": %u, \"input_dim\": %u, \"output_dim\": %u, \"approx_type\": %d, \"num_active\": %u, "
+         "\"learn_scale\": %d, \"learn_bias\": %d,\n",
+         model.getNumData(), model.getInputDim(), model.getOutputDim(), model.getApproximationType(), model.getNumActive(),
+         model.isOutputScaleLearnt() ? 1 : 0, model.isOutputBiasLearnt() ? 1 : 0);
+  printf("\"scale\": [");
+  for(unsigned int j = 0; j < model.getOutputDim(); j++)
+    printf("%s%.17g", j ? ", " : "", model.getScaleVal(j));
+  printf("],\n\"bias\": [");
+  for(unsigned int j = 0; j < model.getOutputDim(); j++)
+    printf("%s%.17g", j ? ", " : "", model.getBiasVal(j));
+  const CKern* kern = model.getKernel();
+  printf("],\n\"kern_type\": \"%s\", \"kern_params\": [", kern->getType().c_str());
+  for(unsigned int i = 0; i < kern->getNumParams(); i++)
+    printf("%s%.17g", i ? ", " : "", kern->getParam(i));
+  printf("],\n");
+  GpcKernBridge bridge;
+  if(bridge.sync(kern, model.getInputDim()))
+  {
+    printf("\"types\": [");
+    for(int i = 0; i < bridge.numComps(); i++)
+      printf("%s%d", i ? ", " : "", bridge.comps()[i].type);
+    printf("], \"nparams\": [");
+    for(int i = 0; i < bridge.numComps(); i++)
+      printf("%s%d", i ? ", " : "", bridge.comps()[i].nparams);
+    printf("], \"degree\": [");
+    for(int i = 0; i < bridge.numComps(); i++)
+      printf("%s%.17g", i ? ", " : "", bridge.comps()[i].degree);
+    printf("],\n");
+  }
+  printf("\"prior_log_prob\": %.17g,\n", kern->priorLogProb());
+  const CNoise* noise = model.*driverMemberOf(DriverNoiseTag());
+  printf("\"noise_type\": \"%s\", \"noise_params\": [", noise->getType().c_str());
+  for(unsigned int i = 0; i < noise->getNumParams(); i++)
+    printf("%s%.17g", i ? ", " : "", noise->getParam(i));
+  printf("]}\n");
+}
+
+static int runModelWrite(unsigned int N, unsigned int D, unsigned int d, const std::string& spec, bool scaleLearnt, bool prior,
+                         const std::string& path)
+{
+  CMatrix X(N, D), y(N, d);
+  for(unsigned int j = 0; j < D; j++)
+    for(unsigned int i = 0; i < N; i++)
+      X.setVal(normal01(), i, j);
+  for(unsigned int j = 0; j < d; j++)
+    for(unsigned int i = 0; i < N; i++)
+      y.setVal(sin(X.getVal(i, 0) + 0.5 * j) + 0.1 * normal01(), i, j);
+  // "single:rbf" = a model whose kernel is ONE kernel object, not a compound of one (readKernFromStream handles both)
+  CCmpndKern cmpnd(X);
+  CKern* pk = &cmpnd;
+  if(spec.find("single:") == 0)
+  {
+    pk = makeComponent(spec.substr(7), D);
+    for(unsigned int i = 0; i < pk->getNumParams(); i++)
+      pk->setTransParam(0.3 * sin(1.0 + 2.0 * i) - 0.2, i);
+  }
+  else
+    buildKernel(cmpnd, spec, D, prior);
+  CKern& kern = *pk;
+  // values that exercise the text format: an integer, a power of two below one (written 0x1p-2: no '.', the reference
+  // reads it back with atoi as 0, CMatrix.cpp:1081-1085), a negative number, a subnormal-free tiny one
+  CMatrix bias(1, d), scale(1, d);
+  for(unsigned int j = 0; j < d; j++)
+  {
+    bias.setVal(j == 0 ? -0.23280985888136582 : (j == 1 ? 0.25 : 3.0), j);
+    scale.setVal(scaleLearnt ? 1.3 + 0.2 * j : 1.0, j);
+  }
+  CGaussianNoise noise(&y);
+  CGp model(&kern, &noise, &X, CGp::FTC, 0, 0);
+  model.setScale(scale);
+  model.setBias(bias);
+  model.updateM();
+  model.setOutputScaleLearnt(scaleLearnt);
+  writeGpToFile(model, path, "written by the reference (cgp_b200_check modelwrite)");
+  dumpModel(model);
+  return 0;
+}
+
+static int runModelRead(const std::string& path)
+{
+  CGp* model = readGpFromFile(path, 0);
+  dumpModel(*model);
+  return 0;
+}
+
 // setOptParams(theta) -> logLikelihoodGradient(g): one evaluation as SURVEY 8(d) M1 defines it, through the C++ class
 static int runBench(unsigned int N, unsigned int D, int reps, const std::string& spec)
 {
@@ -354,6 +467,10 @@ int main(int argc, char** argv)
       return runGp(N, D, d, spec, scale, prior, iters);
     if(mode == "gplvm")
       return runGplvm(N, D, d, spec, scale, prior, iters);
+    if(mode == "modelwrite")
+      return runModelWrite(N, D, d, spec, scale, prior, argc > 9 ? argv[9] : "model.txt");
+    if(mode == "modelread")
+      return runModelRead(spec);
     if(mode == "bridge")
       return runBridge(N, D, spec, prior);
     if(mode == "bench")
