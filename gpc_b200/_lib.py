@@ -21,15 +21,31 @@ class KComp(C.Structure):
 GPC_MAX_COMPONENTS, GPC_MAX_PARAMS, GPC_MODEL_MAX_OUT = 16, 288, 256
 
 
+class KernSpec(C.Structure):
+    """gpc_kern_spec of include/gpc_b200.h"""
+    _fields_ = [("top_is_cmpnd", C.c_int), ("input_dim", C.c_int), ("ncomp", C.c_int),
+                ("type", C.c_int * GPC_MAX_COMPONENTS), ("nparams", C.c_int * GPC_MAX_COMPONENTS),
+                ("degree", C.c_double * GPC_MAX_COMPONENTS), ("params", C.c_double * GPC_MAX_PARAMS)]
+
+
+class NoiseSpec(C.Structure):
+    """gpc_noise_spec of include/gpc_b200.h"""
+    _fields_ = [("type", C.c_char * 16), ("output_dim", C.c_int), ("nparams", C.c_int),
+                ("params", C.c_double * (2 * GPC_MODEL_MAX_OUT + 8))]
+
+
 class GpModel(C.Structure):
     """gpc_gp_model of include/gpc_b200.h (a GP model file, CGp.cpp:1605-1682)"""
     _fields_ = [("num_data", C.c_int64), ("input_dim", C.c_int), ("output_dim", C.c_int), ("approx_type", C.c_int),
-                ("num_active", C.c_uint), ("learn_scale", C.c_int), ("learn_bias", C.c_int), ("top_is_cmpnd", C.c_int),
-                ("kern_input_dim", C.c_int), ("ncomp", C.c_int), ("type", C.c_int * GPC_MAX_COMPONENTS),
-                ("nparams", C.c_int * GPC_MAX_COMPONENTS), ("degree", C.c_double * GPC_MAX_COMPONENTS),
-                ("kern_params", C.c_double * GPC_MAX_PARAMS), ("scale", C.c_double * GPC_MODEL_MAX_OUT),
-                ("bias", C.c_double * GPC_MODEL_MAX_OUT), ("noise_type", C.c_char * 16), ("noise_output_dim", C.c_int),
-                ("noise_nparams", C.c_int), ("noise_params", C.c_double * (GPC_MODEL_MAX_OUT + 8))]
+                ("num_active", C.c_uint), ("learn_scale", C.c_int), ("learn_bias", C.c_int), ("kern", KernSpec),
+                ("scale", C.c_double * GPC_MODEL_MAX_OUT), ("bias", C.c_double * GPC_MODEL_MAX_OUT), ("noise", NoiseSpec)]
+
+
+class GplvmModel(C.Structure):
+    """gpc_gplvm_model of include/gpc_b200.h (a GP-LVM model file, CGplvm.cpp:761-898)"""
+    _fields_ = [("num_data", C.c_int64), ("output_dim", C.c_int), ("latent_dim", C.c_int),
+                ("latent_regularised", C.c_int), ("back_constrained", C.c_int), ("dynamics_learnt", C.c_int),
+                ("has_labels", C.c_int), ("kern", KernSpec), ("noise", NoiseSpec)]
 
 
 class GpcError(RuntimeError):
@@ -57,7 +73,8 @@ SYMBOLS = [
     "gpc_eval", "gpc_download", "gpc_last_timings", "gpc_last_enqueue_ms", "gpc_dpotrf", "gpc_dpotri", "gpc_dtrsm", "gpc_dsyrk",
     "gpc_dgemm", "gpc_dsymv", "gpc_bench_dmma_peak", "gpc_bench_syrk", "gpc_ctx_set_profile", "gpc_last_gemm_profile", "gpc_last_gemm_profile_split", "gpc_bench_gemm", "gpc_dev_create", "gpc_dev_destroy", "gpc_dev_set_stream",
     "gpc_bench_leaf", "gpc_ctx_dims", "gpc_gp_optimise_scg", "gpc_scg_minimise", "gpc_svml_dims", "gpc_svml_read", "gpc_set_gemm_engine", "gpc_gemm_engine_slices", "gpc_gemm_check", "gpc_oz_slice_check",
-    "gpc_gp_model_read", "gpc_gp_model_write", "gpc_gp_model_check_roundtrip",
+    "gpc_gp_model_read", "gpc_gp_model_write", "gpc_gp_model_check_roundtrip", "gpc_gplvm_model_read",
+    "gpc_gplvm_model_write",
     "gpc_dev_launch_count", "gpc_dev_potrf", "gpc_dev_trsm", "gpc_dev_gemm", "gpc_dev_kbuild_cols", "gpc_dev_grad_cols",
 ]
 
@@ -143,6 +160,9 @@ def lib():
     L.gpc_gp_model_read.argtypes = [C.c_char_p, C.POINTER(GpModel)]
     L.gpc_gp_model_write.argtypes = [C.c_char_p, C.POINTER(GpModel), C.c_char_p]
     L.gpc_gp_model_check_roundtrip.argtypes = [C.POINTER(GpModel), c_int_p, c_double_p]
+    L.gpc_gplvm_model_read.argtypes = [C.c_char_p, C.POINTER(GplvmModel), C.c_void_p, i64, C.c_void_p, i64, C.c_void_p]
+    L.gpc_gplvm_model_write.argtypes = [C.c_char_p, C.POINTER(GplvmModel), C.c_void_p, i64, C.c_void_p, i64, C.c_void_p,
+                                        C.c_char_p]
     L.gpc_bench_leaf.argtypes = [C.c_int, C.c_int, c_double_p, C.c_void_p]
     L.gpc_oz_slice_check.argtypes = [C.c_int, i64, i64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gpc_gemm_check.argtypes = [C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,

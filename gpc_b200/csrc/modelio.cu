@@ -1,5 +1,7 @@
-// modelio.cu -- GP model files ("on-disk formats"): the text format `gp learn` writes and
-// `gp display / gnuplot / relearn` read.  Host code only.  Follows, field by field,
+// modelio.cu -- GP and GP-LVM model files ("on-disk formats"): the text formats `gp learn` /
+// `gplvm learn` write and `gp display / gnuplot / relearn`, `gplvm display / gnuplot` read.  Host code only.  Follows,
+// field by field,
+//   CGplvm::writeParamsToStream / readParamsFromStream, writeGplvmToFile           CGplvm.cpp:761-921
 //   CStreamInterface::toStream / fromStream, readStringFromStream, writeToStream   CNdlInterfaces.h:21-175
 //   CGp::writeParamsToStream / readParamsFromStream                                CGp.cpp:1605-1666
 //   CMatrix::writeParamsToStream / readParamsFromStream / toUnheadedStream          CMatrix.cpp:1057-1097, 1158-1172
@@ -140,7 +142,7 @@ const char* kern_name_of(int type) {
 
 // one non-compound kernel after its "type=" line: CKern::readParamsFromStream (CKern.cpp:4260-4278), CPolyKern's
 // (CKern.cpp:2685-2705)
-bool read_leaf(Reader& r, int type, gpc_gp_model* m, int* poff) {
+bool read_leaf(Reader& r, int type, gpc_kern_spec* m, int* poff) {
   if (m->ncomp >= GPC_MAX_COMPONENTS) return r.fail("too many kernel components");
   long inDim, nPar;
   if (!r.field_long("inputDim", &inDim) || !r.field_long("numParams", &nPar)) return false;
@@ -159,19 +161,19 @@ bool read_leaf(Reader& r, int type, gpc_gp_model* m, int* poff) {
   m->type[c] = type;
   m->nparams[c] = (int)nPar;
   m->degree[c] = degree;
-  for (long i = 0; i < nPar; i++) m->kern_params[*poff + i] = par[(size_t)i];
+  for (long i = 0; i < nPar; i++) m->params[*poff + i] = par[(size_t)i];
   *poff += (int)nPar;
-  if (m->kern_input_dim == 0) m->kern_input_dim = (int)inDim;
+  if (m->input_dim == 0) m->input_dim = (int)inDim;
   return true;
 }
 
 // readKernFromStream (CKern.cpp:4192-4259)
-bool read_kern(Reader& r, gpc_gp_model* m) {
+bool read_kern(Reader& r, gpc_kern_spec* m) {
   std::string t;
   if (!r.version() || !r.expect("baseType", "kern") || !r.field("type", t)) return false;
   int poff = 0;
   m->ncomp = 0;
-  m->kern_input_dim = 0;
+  m->input_dim = 0;
   if (t == "cmpnd") {  // CComponentKern::readParamsFromStream (CKern.cpp:94-113)
     long inDim, nPar, nKern;
     if (!r.field_long("inputDim", &inDim) || !r.field_long("numParams", &nPar) || !r.field_long("numKerns", &nKern)) return false;
@@ -183,13 +185,33 @@ bool read_kern(Reader& r, gpc_gp_model* m) {
       if (type < 0) return r.fail("kernel type " + ct + " is outside the device path");
       if (!read_leaf(r, type, m, &poff)) return false;
     }
-    m->kern_input_dim = (int)inDim;
+    m->input_dim = (int)inDim;
     return true;
   }
   int type = kern_type_of(t);
   if (type < 0) return r.fail("kernel type " + t + " is outside the device path");
   m->top_is_cmpnd = 0;
   return read_leaf(r, type, m, &poff);
+}
+
+// readNoiseFromStream + CNoise::readParamsFromStream (CNoise.cpp:1813-1836, 286-305)
+bool read_noise(Reader& r, gpc_noise_spec* n) {
+  std::string nt;
+  long v, rows, cols;
+  if (!r.version() || !r.expect("baseType", "noise") || !r.field("type", nt)) return false;
+  if (nt != "probit" && nt != "ncnm" && nt != "gaussian" && nt != "ordered" && nt != "scale")
+    return r.fail("unknown noise type " + nt);
+  snprintf(n->type, sizeof n->type, "%s", nt.c_str());
+  if (!r.field_long("outputDim", &v)) return false;
+  n->output_dim = (int)v;
+  if (!r.field_long("numParams", &v)) return false;
+  if (v < 0 || v > (long)(sizeof n->params / sizeof n->params[0])) return r.fail("noise numParams out of range");
+  n->nparams = (int)v;
+  std::vector<double> vals;
+  if (!r.matrix(vals, &rows, &cols)) return false;
+  if (rows * cols != n->nparams) return r.fail("number of noise parameters in file does not match");
+  for (int j = 0; j < n->nparams; j++) n->params[j] = vals[(size_t)j];
+  return true;
 }
 
 // ---- writer -----------------------------------------------------------------------------------------------------
@@ -222,6 +244,27 @@ double reread(double v) {
   return strchr(buf, '.') ? atof(buf) : (double)atoi(buf);
 }
 
+int check_kern_noise(const gpc_kern_spec* k, const gpc_noise_spec* n, const char* who) {
+  if (k->ncomp < 1 || k->ncomp > GPC_MAX_COMPONENTS || (!k->top_is_cmpnd && k->ncomp != 1) || n->nparams < 0 ||
+      n->nparams > (int)(sizeof n->params / sizeof n->params[0])) {
+    set_error(std::string(who) + ": sizes out of range");
+    return GPC_ERR_ARG;
+  }
+  int tot = 0;
+  for (int c = 0; c < k->ncomp; c++) {
+    if (!kern_name_of(k->type[c]) || k->nparams[c] != gpc_kern_nparams(k->type[c], k->input_dim)) {
+      set_error(std::string(who) + ": kernel component type / parameter count");
+      return GPC_ERR_ARG;
+    }
+    tot += k->nparams[c];
+  }
+  if (tot > GPC_MAX_PARAMS) {
+    set_error(std::string(who) + ": too many kernel parameters");
+    return GPC_ERR_ARG;
+  }
+  return GPC_OK;
+}
+
 int check_model(const gpc_gp_model* m, const char* who) {
   if (!m) {
     set_error(std::string(who) + ": null model");
@@ -231,24 +274,43 @@ int check_model(const gpc_gp_model* m, const char* who) {
     set_error(std::string(who) + ": sparse approximations are not supported");
     return GPC_ERR_ARG;
   }
-  if (m->output_dim < 1 || m->output_dim > GPC_MODEL_MAX_OUT || m->ncomp < 1 || m->ncomp > GPC_MAX_COMPONENTS ||
-      m->noise_nparams < 0 || m->noise_nparams > GPC_MODEL_MAX_OUT + 8 || (!m->top_is_cmpnd && m->ncomp != 1)) {
+  if (m->output_dim < 1 || m->output_dim > GPC_MODEL_MAX_OUT) {
     set_error(std::string(who) + ": sizes out of range");
     return GPC_ERR_ARG;
   }
+  return check_kern_noise(&m->kern, &m->noise, who);
+}
+
+// readKernFromStream's counterpart: CComponentKern / CKern / CPolyKern writeParamsToStream (CKern.cpp:114-126, 15-26,
+// 2668-2684)
+void put_kern(FILE* f, const gpc_kern_spec* k) {
   int tot = 0;
-  for (int c = 0; c < m->ncomp; c++) {
-    if (!kern_name_of(m->type[c]) || m->nparams[c] != gpc_kern_nparams(m->type[c], m->kern_input_dim)) {
-      set_error(std::string(who) + ": kernel component type / parameter count");
-      return GPC_ERR_ARG;
+  for (int c = 0; c < k->ncomp; c++) tot += k->nparams[c];
+  if (k->top_is_cmpnd) {
+    fputs(NESTED_VERSION, f);
+    fprintf(f, "baseType=kern\ntype=cmpnd\ninputDim=%d\nnumParams=%d\nnumKerns=%d\n", k->input_dim, tot, k->ncomp);
+  }
+  int poff = 0;
+  for (int c = 0; c < k->ncomp; c++) {
+    fputs(NESTED_VERSION, f);
+    fprintf(f, "baseType=kern\ntype=%s\ninputDim=%d\nnumParams=%d\n", kern_name_of(k->type[c]), k->input_dim, k->nparams[c]);
+    if (k->type[c] == GPC_KERN_POLY) {
+      const double deg = k->degree[c];
+      if ((deg - (double)(int)deg) == 0.0)
+        fprintf(f, "degree=%d\n", (int)deg);
+      else
+        fprintf(f, "degree=%a\n", deg);
     }
-    tot += m->nparams[c];
+    put_matrix(f, k->params + poff, 1, k->nparams[c]);
+    fputs("numPriors=0\n", f);
+    poff += k->nparams[c];
   }
-  if (tot > GPC_MAX_PARAMS) {
-    set_error(std::string(who) + ": too many kernel parameters");
-    return GPC_ERR_ARG;
-  }
-  return GPC_OK;
+}
+// CNoise::writeParamsToStream (CNoise.cpp:275-285)
+void put_noise(FILE* f, const gpc_noise_spec* n) {
+  fputs(NESTED_VERSION, f);
+  fprintf(f, "baseType=noise\ntype=%s\noutputDim=%d\nnumParams=%d\n", n->type, n->output_dim, n->nparams);
+  put_matrix(f, n->params, 1, n->nparams);
 }
 
 }  // namespace
@@ -305,29 +367,8 @@ int gpc_gp_model_read(const char* path, gpc_gp_model* m) {
       break;
     }
     for (int j = 0; j < m->output_dim; j++) m->bias[j] = vals[(size_t)j];
-    if (!read_kern(r, m)) break;
-    // readNoiseFromStream + CNoise::readParamsFromStream (CNoise.cpp:1813-1836, 286-305)
-    std::string nt;
-    if (!r.version() || !r.expect("baseType", "noise") || !r.field("type", nt)) break;
-    if (nt != "probit" && nt != "ncnm" && nt != "gaussian" && nt != "ordered" && nt != "scale") {
-      r.fail("unknown noise type " + nt);
-      break;
-    }
-    snprintf(m->noise_type, sizeof m->noise_type, "%s", nt.c_str());
-    if (!r.field_long("outputDim", &v)) break;
-    m->noise_output_dim = (int)v;
-    if (!r.field_long("numParams", &v)) break;
-    if (v < 0 || v > GPC_MODEL_MAX_OUT + 8) {
-      r.fail("noise numParams out of range");
-      break;
-    }
-    m->noise_nparams = (int)v;
-    if (!r.matrix(vals, &rows, &cols)) break;
-    if (rows * cols != m->noise_nparams) {
-      r.fail("number of noise parameters in file does not match");
-      break;
-    }
-    for (int j = 0; j < m->noise_nparams; j++) m->noise_params[j] = vals[(size_t)j];
+    if (!read_kern(r, &m->kern)) break;
+    if (!read_noise(r, &m->noise)) break;
     ok = true;
   } while (false);
   if (!ok) {
@@ -358,31 +399,8 @@ int gpc_gp_model_write(const char* path, const gpc_gp_model* m, const char* comm
           m->learn_scale ? 1 : 0, m->learn_bias ? 1 : 0);
   put_matrix(f, m->scale, 1, m->output_dim);
   put_matrix(f, m->bias, 1, m->output_dim);
-  int tot = 0;
-  for (int c = 0; c < m->ncomp; c++) tot += m->nparams[c];
-  if (m->top_is_cmpnd) {  // CComponentKern::writeParamsToStream (CKern.cpp:114-126)
-    fputs(NESTED_VERSION, f);
-    fprintf(f, "baseType=kern\ntype=cmpnd\ninputDim=%d\nnumParams=%d\nnumKerns=%d\n", m->kern_input_dim, tot, m->ncomp);
-  }
-  int poff = 0;
-  for (int c = 0; c < m->ncomp; c++) {  // CKern::writeParamsToStream (CKern.cpp:15-26), CPolyKern's (CKern.cpp:2668-2684)
-    fputs(NESTED_VERSION, f);
-    fprintf(f, "baseType=kern\ntype=%s\ninputDim=%d\nnumParams=%d\n", kern_name_of(m->type[c]), m->kern_input_dim, m->nparams[c]);
-    if (m->type[c] == GPC_KERN_POLY) {
-      const double deg = m->degree[c];
-      if ((deg - (double)(int)deg) == 0.0)
-        fprintf(f, "degree=%d\n", (int)deg);
-      else
-        fprintf(f, "degree=%a\n", deg);
-    }
-    put_matrix(f, m->kern_params + poff, 1, m->nparams[c]);
-    fputs("numPriors=0\n", f);
-    poff += m->nparams[c];
-  }
-  // CNoise::writeParamsToStream (CNoise.cpp:275-285)
-  fputs(NESTED_VERSION, f);
-  fprintf(f, "baseType=noise\ntype=%s\noutputDim=%d\nnumParams=%d\n", m->noise_type, m->noise_output_dim, m->noise_nparams);
-  put_matrix(f, m->noise_params, 1, m->noise_nparams);
+  put_kern(f, &m->kern);
+  put_noise(f, &m->noise);
   const bool bad = ferror(f) != 0;
   if (fclose(f) != 0 || bad) {
     set_error(std::string("gpc_gp_model_write: write error on ") + path);
@@ -406,10 +424,164 @@ int gpc_gp_model_check_roundtrip(const gpc_gp_model* m, int* nlost, double* firs
   for (int j = 0; j < m->output_dim; j++) see(m->scale[j]);
   for (int j = 0; j < m->output_dim; j++) see(m->bias[j]);
   int tot = 0;
-  for (int c = 0; c < m->ncomp; c++) tot += m->nparams[c];
-  for (int i = 0; i < tot; i++) see(m->kern_params[i]);
-  for (int i = 0; i < m->noise_nparams; i++) see(m->noise_params[i]);
+  for (int c = 0; c < m->kern.ncomp; c++) tot += m->kern.nparams[c];
+  for (int i = 0; i < tot; i++) see(m->kern.params[i]);
+  for (int i = 0; i < m->noise.nparams; i++) see(m->noise.params[i]);
   if (nlost) *nlost = lost;
   if (first_lost) *first_lost = first;
+  return GPC_OK;
+}
+
+// ---- GP-LVM model files --------------------------------------------------------------------------------------------
+int gpc_gplvm_model_read(const char* path, gpc_gplvm_model* m, double* Y, int64_t ldy, double* X, int64_t ldx, int* labels) {
+  if (!path || !m) {
+    set_error("gpc_gplvm_model_read: null argument");
+    return GPC_ERR_ARG;
+  }
+  memset(m, 0, sizeof *m);
+  Reader r(path);
+  if (!r.f) {
+    set_error(std::string("gpc_gplvm_model_read: cannot open ") + path);
+    return GPC_ERR_ARG;
+  }
+  bool ok = false;
+  do {
+    long v;
+    // CStreamInterface::fromStream + CGplvm::readParamsFromStream (CGplvm.cpp:802-898)
+    if (!r.version() || !r.expect("baseType", "dataModel") || !r.expect("type", "gplvm")) break;
+    if (!r.field_long("numData", &v)) break;
+    m->num_data = v;
+    if (!r.field_long("outputDim", &v)) break;
+    m->output_dim = (int)v;
+    if (!r.field_long("inputDim", &v)) break;
+    m->latent_dim = (int)v;
+    if (!r.field_long("latentRegularised", &v)) break;
+    m->latent_regularised = v != 0;
+    if (!r.field_long("backConstrained", &v)) break;
+    m->back_constrained = v != 0;
+    if (!r.field_long("dynamicsLearnt", &v)) break;
+    m->dynamics_learnt = v != 0;
+    if (m->back_constrained || m->dynamics_learnt) {
+      r.fail("GP-LVM models with back constraints or dynamics are not supported");
+      break;
+    }
+    if (m->num_data < 0 || m->output_dim < 1 || m->output_dim > GPC_MODEL_MAX_OUT || m->latent_dim < 1) {
+      r.fail("sizes out of range");
+      break;
+    }
+    if (!read_kern(r, &m->kern)) break;
+    if (!read_noise(r, &m->noise)) break;
+    // "Y:d,X:q[,labels:1]" (CGplvm.cpp:843-872)
+    std::string l;
+    if (!r.line(l)) {
+      r.fail("end of file when expecting the Y:,X: line");
+      break;
+    }
+    bool bad = false;
+    size_t pos = 0;
+    while (pos <= l.size() && !bad) {
+      size_t e = l.find(',', pos);
+      if (e == std::string::npos) e = l.size();
+      std::string tok = l.substr(pos, e - pos);
+      pos = e + 1;
+      if (tok.empty()) continue;
+      size_t c = tok.find(':');
+      std::string key = tok.substr(0, c);
+      int val = (c == std::string::npos) ? 0 : atoi(tok.c_str() + c + 1);
+      if (key == "Y")
+        bad = val != m->output_dim;
+      else if (key == "X")
+        bad = val != m->latent_dim;
+      else if (key == "labels") {
+        m->has_labels = 1;
+        bad = val != 1;
+      } else
+        bad = true;
+    }
+    if (bad) {
+      r.fail("file format error in the Y:,X: line");
+      break;
+    }
+    if (!Y && !X) {  // header only
+      ok = true;
+      break;
+    }
+    if (!Y || !X || ldy < m->num_data || ldx < m->num_data) {
+      r.fail("Y and X buffers (ld >= numData) are both required");
+      break;
+    }
+    const int d = m->output_dim, q = m->latent_dim;
+    bool rows_ok = true;
+    for (int64_t i = 0; i < m->num_data && rows_ok; i++) {
+      if (!r.line(l)) {
+        rows_ok = r.fail("end of file inside the data rows");
+        break;
+      }
+      std::vector<std::string> tok;
+      size_t last = l.find_first_not_of(' ', 0), p2 = l.find_first_of(' ', last);
+      while (p2 != std::string::npos || last != std::string::npos) {
+        tok.push_back(l.substr(last, p2 - last));
+        last = l.find_first_not_of(' ', p2);
+        p2 = l.find_first_of(' ', last);
+      }
+      if ((int)tok.size() < d + q + (m->has_labels ? 1 : 0)) {  // the reference indexes past the end here
+        rows_ok = r.fail("too few values in a data row");
+        break;
+      }
+      for (int j = 0; j < d; j++) Y[i + (int64_t)j * ldy] = atof(tok[(size_t)j].c_str());
+      for (int j = 0; j < q; j++) X[i + (int64_t)j * ldx] = atof(tok[(size_t)(d + j)].c_str());
+      if (m->has_labels && labels) labels[i] = atoi(tok[(size_t)(d + q)].c_str());
+    }
+    ok = rows_ok;
+  } while (false);
+  if (!ok) {
+    std::string e = r.err.empty() ? std::string("gpc_gplvm_model_read: failed on ") + path : r.err;
+    size_t at = e.find("gpc_gp_model_read");
+    if (at != std::string::npos) e.replace(at, strlen("gpc_gp_model_read"), "gpc_gplvm_model_read");
+    set_error(e);
+    return GPC_ERR_ARG;
+  }
+  return GPC_OK;
+}
+
+int gpc_gplvm_model_write(const char* path, const gpc_gplvm_model* m, const double* Y, int64_t ldy, const double* X,
+                          int64_t ldx, const int* labels, const char* comment) {
+  if (!path || !m || !Y || !X) {
+    set_error("gpc_gplvm_model_write: null argument");
+    return GPC_ERR_ARG;
+  }
+  if (m->back_constrained || m->dynamics_learnt || m->num_data < 0 || m->output_dim < 1 || m->output_dim > GPC_MODEL_MAX_OUT ||
+      m->latent_dim < 1 || ldy < m->num_data || ldx < m->num_data || (m->has_labels && !labels)) {
+    set_error("gpc_gplvm_model_write: unsupported model or sizes out of range");
+    return GPC_ERR_ARG;
+  }
+  int rc = check_kern_noise(&m->kern, &m->noise, "gpc_gplvm_model_write");
+  if (rc != GPC_OK) return rc;
+  FILE* f = fopen(path, "wb");
+  if (!f) {
+    set_error(std::string("gpc_gplvm_model_write: cannot open ") + path);
+    return GPC_ERR_ARG;
+  }
+  // writeGplvmToFile sets ios::scientific BEFORE toStream adds ios::fixed (CGplvm.cpp:908-921): here even the outermost
+  // version is hexfloat; the data rows are plain `out << value`, i.e. "%a" for every entry, integers included
+  if (comment && comment[0]) fprintf(f, "# %s\n", comment);
+  fputs(NESTED_VERSION, f);
+  fprintf(f, "baseType=dataModel\ntype=gplvm\nnumData=%lld\noutputDim=%d\ninputDim=%d\n", (long long)m->num_data, m->output_dim,
+          m->latent_dim);
+  fprintf(f, "latentRegularised=%d\nbackConstrained=0\ndynamicsLearnt=0\n", m->latent_regularised ? 1 : 0);
+  put_kern(f, &m->kern);
+  put_noise(f, &m->noise);
+  fprintf(f, "Y:%d,X:%d%s\n", m->output_dim, m->latent_dim, m->has_labels ? ",labels:1" : "");
+  for (int64_t i = 0; i < m->num_data; i++) {
+    for (int j = 0; j < m->output_dim; j++) fprintf(f, "%a ", Y[i + (int64_t)j * ldy]);
+    for (int j = 0; j < m->latent_dim; j++) fprintf(f, "%a ", X[i + (int64_t)j * ldx]);
+    if (m->has_labels) fprintf(f, "%d", labels[i]);
+    fputc('\n', f);
+  }
+  const bool bad = ferror(f) != 0;
+  if (fclose(f) != 0 || bad) {
+    set_error(std::string("gpc_gplvm_model_write: write error on ") + path);
+    return GPC_ERR_ARG;
+  }
   return GPC_OK;
 }

@@ -245,27 +245,51 @@ int gpc_svml_read(const char* path, double* X, int64_t ldx, double* y, int64_t n
  * as 0.  gpc_gp_model_check_roundtrip counts the values of a model that would be lost that way (*first_lost = the first).
  * A file with priors is rejected, as the reference's own reader rejects it (CDist.cpp:4-10 vs 338-357). */
 #define GPC_MODEL_MAX_OUT 256
+typedef struct gpc_kern_spec {       /* a kernel object as the stream holds it (readKernFromStream, CKern.cpp:4192-4259) */
+  int top_is_cmpnd;                  /* 1: CCmpndKern of ncomp components; 0: a single kernel object (ncomp = 1) */
+  int input_dim;
+  int ncomp;
+  int type[GPC_MAX_COMPONENTS];      /* gpc_kern_type */
+  int nparams[GPC_MAX_COMPONENTS];
+  double degree[GPC_MAX_COMPONENTS]; /* POLY only */
+  double params[GPC_MAX_PARAMS];     /* NATURAL values, component order (CKern::getParams) */
+} gpc_kern_spec;
+typedef struct gpc_noise_spec {      /* a noise object as the stream holds it (CNoise.cpp:275-305, 1813-1836) */
+  char type[16];                     /* "gaussian" for gp learn, "scale" for gplvm learn */
+  int output_dim, nparams;
+  double params[2 * GPC_MODEL_MAX_OUT + 8]; /* gaussian: bias_1..bias_d, sigma2; scale: bias_1..bias_d, scale_1..scale_d */
+} gpc_noise_spec;
 typedef struct gpc_gp_model {
   int64_t num_data;
   int input_dim, output_dim;
   int approx_type;         /* CGp::FTC = 0 (field "sparseApproximation"); anything else is rejected */
   unsigned int num_active; /* written as is (the CLI leaves 0 or 4294967295 for FTC) */
   int learn_scale, learn_bias;
-  int top_is_cmpnd;        /* 1: CCmpndKern of ncomp components; 0: a single kernel object (ncomp = 1) */
-  int kern_input_dim;
-  int ncomp;
-  int type[GPC_MAX_COMPONENTS];    /* gpc_kern_type */
-  int nparams[GPC_MAX_COMPONENTS];
-  double degree[GPC_MAX_COMPONENTS]; /* POLY only */
-  double kern_params[GPC_MAX_PARAMS]; /* NATURAL values, component order (CKern::getParams) */
+  gpc_kern_spec kern;
   double scale[GPC_MODEL_MAX_OUT], bias[GPC_MODEL_MAX_OUT];
-  char noise_type[16];     /* "gaussian" for gp learn (CNoise.cpp:1821-1833) */
-  int noise_output_dim, noise_nparams;
-  double noise_params[GPC_MODEL_MAX_OUT + 8]; /* gaussian: bias_1..bias_d, sigma2 */
+  gpc_noise_spec noise;
 } gpc_gp_model;
 int gpc_gp_model_read(const char* path, gpc_gp_model* out);
 int gpc_gp_model_write(const char* path, const gpc_gp_model* model, const char* comment);
 int gpc_gp_model_check_roundtrip(const gpc_gp_model* model, int* nlost, double* first_lost);
+
+/* GP-LVM model files (CGplvm::writeParamsToStream / readParamsFromStream CGplvm.cpp:761-898, writeGplvmToFile :908-921):
+ * header fields, kernel, CScaleNoise, then one text row per data point holding its d targets, q latent coordinates and
+ * (optionally) an integer label -- all hexfloat, all read back with atof (no atoi rule here).  Plain GP-LVMs only: files
+ * with back constraints or a dynamics kernel are rejected.  Y (num_data x output_dim) and X (num_data x latent_dim) are
+ * caller-owned column-major buffers; labels (num_data ints) may be NULL.  gpc_gplvm_model_read with Y == X == NULL fills
+ * the header only (sizes for the buffers). */
+typedef struct gpc_gplvm_model {
+  int64_t num_data;
+  int output_dim, latent_dim;
+  int latent_regularised, back_constrained, dynamics_learnt;
+  int has_labels;
+  gpc_kern_spec kern;
+  gpc_noise_spec noise;
+} gpc_gplvm_model;
+int gpc_gplvm_model_read(const char* path, gpc_gplvm_model* out, double* Y, int64_t ldy, double* X, int64_t ldx, int* labels);
+int gpc_gplvm_model_write(const char* path, const gpc_gplvm_model* model, const double* Y, int64_t ldy, const double* X,
+                          int64_t ldx, const int* labels, const char* comment);
 
 /* ---- fp64 GEMM engine selection -------------------------------------------------------------------- */
 /* The dsyrk_/dgemm_ work below dpotrf_/dpotri_ (lapack.h:59-73) runs on one of two engines:

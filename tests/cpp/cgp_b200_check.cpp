@@ -10,6 +10,8 @@
 //   cgp_b200_check bridge N D 0 seed kern1,kern2,... 0 [prior]   GpcKernBridge alone (host only)
 //   cgp_b200_check modelwrite N D d seed kern1,kern2,... scale prior path   the REFERENCE writes a gp model file (CGp.cpp:1640-1666)
 //   cgp_b200_check modelread 0 0 0 0 path                                   the REFERENCE reads one and prints what it holds
+//   cgp_b200_check lvmwrite N q d seed kern1,kern2,... labels 0 path        the REFERENCE writes a gplvm model file (CGplvm.cpp:761-921)
+//   cgp_b200_check lvmread 0 0 0 0 path                                     the REFERENCE reads one
 //   cgp_b200_check bench N D reps seed kern1,kern2,...      evaluations per second through CGpB200 alone (the metric of
 //                                                           bench.py, driven the way COptimisable drives a model)
 #include <cstdio>
@@ -389,6 +391,76 @@ static int runModelWrite(unsigned int N, unsigned int D, unsigned int d, const s
   return 0;
 }
 
+static void dumpLvm(const CGplvm& model)
+{
+  printf("{\"num_data\": %u, \"output_dim\": %d, \"latent_dim\": %d, \"latent_regularised\": %d, \"back_constrained\": %d, "
+         "\"dynamics_learnt\": %d, \"has_labels\": %d,\n",
+         model.getNumData(), model.getNumProcesses(), model.getLatentDim(), model.isLatentRegularised() ? 1 : 0,
+         model.isBackConstrained() ? 1 : 0, model.isDynamicModelLearnt() ? 1 : 0, model.isLabels() ? 1 : 0);
+  printf("\"kern_params\": [");
+  for(unsigned int i = 0; i < model.pkern->getNumParams(); i++)
+    printf("%s%.17g", i ? ", " : "", model.pkern->getParam(i));
+  printf("],\n");
+  GpcKernBridge bridge;
+  if(bridge.sync(model.pkern, model.getLatentDim()))
+  {
+    printf("\"types\": [");
+    for(int i = 0; i < bridge.numComps(); i++)
+      printf("%s%d", i ? ", " : "", bridge.comps()[i].type);
+    printf("],\n");
+  }
+  printf("\"noise_type\": \"%s\", \"noise_params\": [", model.pnoise->getType().c_str());
+  for(unsigned int i = 0; i < model.pnoise->getNumParams(); i++)
+    printf("%s%.17g", i ? ", " : "", model.pnoise->getParam(i));
+  printf("],\n\"Y\": [");
+  for(int j = 0; j < model.getNumProcesses(); j++)
+    for(unsigned int i = 0; i < model.getNumData(); i++)
+      printf("%s%.17g", (i || j) ? ", " : "", model.pnoise->getTarget(i, j));
+  printf("],\n\"X\": [");
+  for(int j = 0; j < model.getLatentDim(); j++)
+    for(unsigned int i = 0; i < model.getNumData(); i++)
+      printf("%s%.17g", (i || j) ? ", " : "", model.pX->getVal(i, j));
+  printf("],\n\"labels\": [");
+  if(model.isLabels())
+    for(unsigned int i = 0; i < model.getNumData(); i++)
+      printf("%s%d", i ? ", " : "", model.getLabel(i));
+  printf("]}\n");
+}
+
+// the REFERENCE builds a GP-LVM (PCA initialisation), optionally labels it, and writes it with writeGplvmToFile
+static int runLvmWrite(unsigned int N, unsigned int q, unsigned int d, const std::string& spec, bool withLabels,
+                       const std::string& path)
+{
+  CMatrix Y(N, d);
+  for(unsigned int j = 0; j < d; j++)
+    for(unsigned int i = 0; i < N; i++)
+      Y.setVal(sin(0.3 * i + j) + (j == 0 && i == 0 ? 0.0 : 0.1 * normal01()) + (i == 1 && j == 1 ? 2.0 : 0.0), i, j);
+  Y.setVal(3.0, 2, 0); // an integer and (below) a power of two: written "%a" here, unlike CMatrix::toUnheadedStream
+  Y.setVal(0.25, 3, 0);
+  CMatrix Xtmp(1, q);
+  CCmpndKern kern(Xtmp);
+  buildKernel(kern, spec, q, false);
+  CScaleNoise noise(&Y);
+  CGplvm model(&kern, &noise, q, 0);
+  if(withLabels)
+  {
+    std::vector<int> labels(N);
+    for(unsigned int i = 0; i < N; i++)
+      labels[i] = (int)(i % 3) - 1;
+    model.setLabels(labels);
+  }
+  writeGplvmToFile(model, path, "written by the reference (cgp_b200_check lvmwrite)");
+  dumpLvm(model);
+  return 0;
+}
+
+static int runLvmRead(const std::string& path)
+{
+  CGplvm* model = readGplvmFromFile(path, 0);
+  dumpLvm(*model);
+  return 0;
+}
+
 static int runModelRead(const std::string& path)
 {
   CGp* model = readGpFromFile(path, 0);
@@ -471,6 +543,10 @@ int main(int argc, char** argv)
       return runModelWrite(N, D, d, spec, scale, prior, argc > 9 ? argv[9] : "model.txt");
     if(mode == "modelread")
       return runModelRead(spec);
+    if(mode == "lvmwrite")
+      return runLvmWrite(N, D, d, spec, scale, argc > 9 ? argv[9] : "lvm.txt");
+    if(mode == "lvmread")
+      return runLvmRead(spec);
     if(mode == "bridge")
       return runBridge(N, D, spec, prior);
     if(mode == "bench")

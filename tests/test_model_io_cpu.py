@@ -147,3 +147,62 @@ def test_comment_lines_and_carriage_returns_are_read_like_the_reference(tmp_path
     seen = _driver("modelread", 0, 0, 0, 0, path)
     _same_values(io.read_gp_model(path), seen)
     assert seen == _driver("modelread", 0, 0, 0, 0, ref_file)
+
+
+# ---- GP-LVM model files (CGplvm.cpp:761-921) ---------------------------------------------------------------------
+def _same_lvm(m, ref):
+    N, d, q = ref["num_data"], ref["output_dim"], ref["latent_dim"]
+    assert (m["num_data"], m["output_dim"], m["latent_dim"]) == (N, d, q)
+    assert int(m["latent_regularised"]) == ref["latent_regularised"]
+    assert int(m["back_constrained"]) == ref["back_constrained"] == 0
+    assert int(m["dynamics_learnt"]) == ref["dynamics_learnt"] == 0
+    assert [CODE[t] for t in m["types"]] == ref["types"]
+    assert list(np.concatenate(m["params"])) == ref["kern_params"]
+    assert m["noise_type"] == ref["noise_type"] == "scale" and list(m["noise_params"]) == ref["noise_params"]
+    assert list(m["Y"].reshape(-1, order="F")) == ref["Y"]       # bit for bit, column-major
+    assert list(m["X"].reshape(-1, order="F")) == ref["X"]
+    assert (list(m["labels"]) if m["labels"] is not None else []) == ref["labels"]
+
+
+# labels always: CGplvm's labelsPresent flag is not initialised by its constructors (CGplvm.cpp:18-36), so the reference's
+# behaviour without setLabels is undefined; gplvm.cpp always sets them (gplvm.cpp:583-586)
+@pytest.mark.parametrize("spec,N,q,d,labels", [("rbf,bias,white", 12, 2, 3, 1), ("rbfard,white", 40, 3, 5, 1),
+                                               ("matern52,lin,bias,white", 25, 2, 12, 1)])
+def test_gplvm_model_files_against_the_reference(tmp_path, spec, N, q, d, labels):
+    ref_file = str(tmp_path / "ref.model")
+    truth = _driver("lvmwrite", N, q, d, 5, spec, labels, 0, ref_file)   # the reference builds (PCA init) and writes
+    seen = _driver("lvmread", 0, 0, 0, 0, ref_file)                      # ... and reads it back
+    assert truth["Y"] == seen["Y"] and truth["X"] == seen["X"]           # hexfloat + atof: this format is lossless
+    m = io.read_gplvm_model(ref_file)
+    _same_lvm(m, seen)
+    ours = str(tmp_path / "ours.model")
+    io.write_gplvm_model(ours, m, "anything")
+    assert _body(ours) == _body(ref_file)                                # byte-identical to writeGplvmToFile
+    assert _driver("lvmread", 0, 0, 0, 0, ours) == seen
+    # the label-free form of the same file (what the writer code emits when labelsPresent is false): own round trip
+    m["labels"] = None
+    io.write_gplvm_model(ours, m)
+    assert "labels" not in open(ours).read()
+    back = io.read_gplvm_model(ours)
+    assert back["labels"] is None and np.array_equal(back["Y"], m["Y"]) and np.array_equal(back["X"], m["X"])
+
+
+def test_gplvm_model_files_the_library_does_not_take(tmp_path):
+    from gpc_b200._lib import GpcError
+    ref_file = str(tmp_path / "ref.model")
+    _driver("lvmwrite", 10, 2, 3, 5, "rbf,white", 1, 0, ref_file)
+    text = open(ref_file).read()
+    bad = str(tmp_path / "bad.model")
+    open(bad, "w").write(text.replace("dynamicsLearnt=0", "dynamicsLearnt=1"))
+    with pytest.raises(GpcError, match="dynamics"):
+        io.read_gplvm_model(bad)
+    open(bad, "w").write(text.replace("Y:3,X:2", "Y:4,X:2"))              # FileFormatError in the reference (CGplvm.cpp:853)
+    with pytest.raises(GpcError, match="Y:,X:"):
+        io.read_gplvm_model(bad)
+    assert _driver("lvmread", 0, 0, 0, 0, bad, ok=False).returncode != 0
+    open(bad, "w").write("\n".join(text.split("\n")[:-4]))                 # rows missing
+    with pytest.raises(GpcError, match="data rows"):
+        io.read_gplvm_model(bad)
+    with pytest.raises(GpcError):                                          # a gp file is not a gplvm file
+        _driver("modelwrite", 25, 2, 1, 5, "rbf,white", 0, 0, ref_file)
+        io.read_gplvm_model(ref_file)
