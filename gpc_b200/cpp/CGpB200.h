@@ -61,6 +61,8 @@ class CGpB200 : public CGp
   unsigned long getNumDeviceEvals() const { return nEvals; }
 
  private:
+  CGpB200(const CGpB200&);            // the object owns a device context: not copyable
+  CGpB200& operator=(const CGpB200&);
   enum { STALE = 0, FACTORED = 1, EVALUATED = 2 };
   void init();
   bool sameInputs() const; // kernel parameters, scale, bias, m, data pointers unchanged since the cached evaluation

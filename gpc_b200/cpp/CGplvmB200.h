@@ -38,6 +38,8 @@ class CGplvmB200 : public CGplvm
   unsigned long getNumDeviceEvals() const { return nEvals; }
 
  private:
+  CGplvmB200(const CGplvmB200&);            // the object owns a device context: not copyable
+  CGplvmB200& operator=(const CGplvmB200&);
   void init();
   void ensureEvaluated() const;
   void fail(int rc) const;
