@@ -8,6 +8,7 @@
 //   cgp_b200_check gp    N D d seed kern1,kern2,... [scale] [prior] [iters]
 //   cgp_b200_check gplvm N q d seed kern1,kern2,... [scale] [prior] [iters]
 //   cgp_b200_check bridge N D 0 seed kern1,kern2,... 0 [prior]   GpcKernBridge alone (host only)
+//   cgp_b200_check sparse N D d seed kern1,kern2,... approx M beta           the REFERENCE's DTC(1) / FITC(2) / DTCVAR(4) ll + gradient
 //   cgp_b200_check modelwrite N D d seed kern1,kern2,... scale prior path   the REFERENCE writes a gp model file (CGp.cpp:1640-1666)
 //   cgp_b200_check modelread 0 0 0 0 path                                   the REFERENCE reads one and prints what it holds
 //   cgp_b200_check lvmwrite N q d seed kern1,kern2,... labels 0 path        the REFERENCE writes a gplvm model file (CGplvm.cpp:761-921)
@@ -296,6 +297,48 @@ static int runBridge(unsigned int N, unsigned int D, const std::string& spec, bo
   return 0;
 }
 
+// ---- sparse approximations: the REFERENCE's DTC / DTCVAR / FITC log-likelihood and gradient on seeded inputs, for
+// oracle/gp_sparse_oracle.py (CGp.cpp:713-735, 766-861, 939-988, 1244-1413)
+static int runSparse(unsigned int N, unsigned int D, unsigned int d, const std::string& spec, int approx, unsigned int M,
+                     double betaVal)
+{
+  CMatrix X(N, D), y(N, d);
+  for(unsigned int j = 0; j < D; j++)
+    for(unsigned int i = 0; i < N; i++)
+      X.setVal(normal01(), i, j);
+  for(unsigned int j = 0; j < d; j++)
+    for(unsigned int i = 0; i < N; i++)
+      y.setVal(sin(X.getVal(i, 0) + 0.5 * j) + 0.1 * normal01(), i, j);
+  CCmpndKern kern(X);
+  buildKernel(kern, spec, D, false);
+  CGaussianNoise noise(&y);
+  CGp model(&kern, &noise, &X, approx, M, 0); // picks M rows of X as inducing inputs (CGp::initVals, CGp.cpp:273-284)
+  CMatrix bias(1, d);
+  for(unsigned int j = 0; j < d; j++)
+  {
+    double sum = 0.0;
+    for(unsigned int i = 0; i < N; i++)
+      sum += y.getVal(i, j);
+    bias.setVal(sum / N, j);
+  }
+  model.setBias(bias);
+  model.updateM();
+  model.setBetaVal(betaVal);
+  CMatrix g(1, model.getOptNumParams()), p(1, model.getOptNumParams());
+  model.getOptParams(p);
+  double ll = model.logLikelihoodGradient(g);
+  printf("{\"approx\": \"%s\", \"N\": %u, \"D\": %u, \"d\": %u, \"M\": %u, \"beta\": %.17g, \"ll\": %.17g,\n",
+         model.getApproximationStr().c_str(), N, D, d, M, model.getBetaVal(), ll);
+  printVec("X", X);
+  printVec("y", y);
+  printVec("bias", bias);
+  printVec("X_u", model.X_u);
+  printVec("params", p);
+  printVec("g", g, true);
+  printf("}\n");
+  return 0;
+}
+
 // ---- model files: the reference as the oracle of gpc_gp_model_read / gpc_gp_model_write (tests/test_model_io_cpu.py)
 namespace
 {
@@ -539,6 +582,8 @@ int main(int argc, char** argv)
       return runGp(N, D, d, spec, scale, prior, iters);
     if(mode == "gplvm")
       return runGplvm(N, D, d, spec, scale, prior, iters);
+    if(mode == "sparse") // sparse N D d seed kernels approx(1 dtc, 2 fitc, 4 dtcvar) M beta
+      return runSparse(N, D, d, spec, argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 10, argc > 9 ? atof(argv[9]) : 10.0);
     if(mode == "modelwrite")
       return runModelWrite(N, D, d, spec, scale, prior, argc > 9 ? argv[9] : "model.txt");
     if(mode == "modelread")

@@ -162,6 +162,45 @@ def random_cases():
     np.savez_compressed(os.path.join(HERE, "random_reference.npz"), **out)
 
 
+SPARSE_CASES = [  # (tag, N, D, d, kernels, approx code of CGp.h:12-19, M, beta)
+    ("dtc_rbf", 60, 2, 1, "rbf,bias,white", 1, 8, 10.0),
+    ("dtc_ard2", 150, 3, 2, "rbfard,lin,white", 1, 12, 25.0),
+    ("dtc_poly", 120, 2, 1, "poly,rbf,bias,white", 1, 10, 5.0),
+    ("fitc_rbf", 60, 2, 1, "rbf,bias,white", 2, 8, 10.0),
+    ("fitc_ard2", 150, 3, 2, "rbfard,lin,white", 2, 12, 25.0),
+    ("fitc_poly", 120, 2, 1, "poly,rbf,bias,white", 2, 10, 5.0),
+    ("dtcvar_rbf", 60, 2, 1, "rbf,bias,white", 4, 8, 10.0),
+    ("dtcvar_ard2", 150, 3, 2, "rbfard,lin,white", 4, 12, 25.0),
+]
+
+
+def sparse_fixtures():
+    """SURVEY 8(f) row 2 (sparse approximations), for oracle/gp_sparse_oracle.py:
+    (1) the reference's MATLAB known answers matfiles/testGpdtc.mat, testGpfitc.mat (testGp.cpp:21-23, 98-150): X, y,
+        inducing inputs, beta, optimiser-space parameters, gradients and log-likelihood;
+    (2) the compiled reference (oracle/_ref/cgp_b200_check sparse: CGp with approxType DTC / FITC / DTCVAR) on seeded
+        inputs -- better conditioned than the MATLAB cases (cond(A) ~ 1e9 there) and covering two outputs, ARD, poly."""
+    import json
+    import subprocess
+    out = {}
+    for name in ("testGpdtc", "testGpfitc"):
+        m = sio.loadmat(MF + name + ".mat", squeeze_me=True, struct_as_record=False)
+        gi = m["gpInfoInit"]
+        out.update({name + "_X": m["X"], name + "_y": np.asarray(m["y"]).reshape(-1, 1), name + "_Xu": gi.X_u,
+                    name + "_beta": float(gi.beta), name + "_params": m["params"], name + "_grads": m["grads"],
+                    name + "_ll": float(m["ll"]), name + "_bias": float(m["bias"]), name + "_scale": float(m["scale"]),
+                    name + "_types": np.array([c.type for c in m["kernInit"].comp])})
+    exe = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "cgp_b200_check")
+    for tag, N, D, d, spec, approx, M, beta in SPARSE_CASES:
+        r = json.loads(subprocess.run([exe, "sparse", str(N), str(D), str(d), "3", spec, str(approx), str(M), str(beta)],
+                                      capture_output=True, text=True, check=True).stdout)
+        out.update({tag + "_X": np.array(r["X"]).reshape(D, N).T, tag + "_y": np.array(r["y"]).reshape(d, N).T,
+                    tag + "_Xu": np.array(r["X_u"]).reshape(D, M).T, tag + "_beta": r["beta"], tag + "_bias": np.array(r["bias"]),
+                    tag + "_params": np.array(r["params"]), tag + "_grads": np.array(r["g"]), tag + "_ll": r["ll"],
+                    tag + "_approx": np.array(r["approx"]), tag + "_types": np.array(spec.split(","))})
+    np.savez_compressed(os.path.join(HERE, "sparse_reference.npz"), **out)
+
+
 def ivm_fixture():
     """examples/unitsquaregp.svml (500 x 2, labels +-1): the data of the reference's IVM walk-through
     (README.md:234, `ivm learn -a 200 -k rbf examples/unitsquaregp.svml`), for tests/test_gpu_shim.py."""
@@ -175,6 +214,7 @@ if __name__ == "__main__":
     gp_fixtures()
     random_cases()
     ivm_fixture()
+    sparse_fixtures()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
