@@ -1,4 +1,4 @@
-"""Multi-rank path on CPU (gloo, world_size 2): checks the distributed SCHEDULE of gpc_b200/dist.py -- block-cyclic
+"""Multi-rank path on CPU (gloo, world sizes 2, 4 and 8): checks the distributed SCHEDULE of gpc_b200/dist.py -- block-cyclic
 ownership, panel broadcasts, the all-gather of the W blocks, the all-reduces -- with a numpy stand-in for the device
 kernels (test double defined here; the package has no CPU backend).  The result must equal the oracle's ll/gradient."""
 import os
