@@ -117,3 +117,22 @@ def test_unmodified_gplvm_front_end_on_the_drop_in_class_falls_through(tmp_path)
         assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     body = lambda p: open(str(tmp_path / p)).read().split("\n", 1)[1]
     assert body("m_ref") == body("m_l2")
+
+
+def test_makefile_builds_the_host_classes_against_the_reference_tree(tmp_path):
+    """gpc_b200/cpp/Makefile: what INTEGRATION.md tells a maintainer to run.  Needs the reference sources, so it runs in
+    the build container only."""
+    ref = os.environ.get("GPC_REFERENCE", "/root/reference")
+    if not os.path.isdir(ref):
+        pytest.skip("reference sources not present")
+    blasmap = os.path.join(ROOT, "oracle", "_ref", "obj", "blasmap.h")
+    extra = ("-include " + blasmap) if os.path.exists(blasmap) else ""
+    out = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "gpc_b200", "cpp"), "BUILD=" + str(tmp_path),
+                          "GPC_REFERENCE=" + ref, "EXTRA_CXXFLAGS=" + extra, "all", "frontends"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    for f in ("libgpc_cgp.a", "gp_dropin.o", "gplvm_dropin.o"):
+        assert os.path.getsize(str(tmp_path / f)) > 0
+    syms = subprocess.run(["nm", "-C", str(tmp_path / "gp_dropin.o")], capture_output=True, text=True).stdout
+    assert "CGpB200::CGpB200(CKern*, CNoise*, CMatrix*, int, unsigned int, int)" in syms    # gp.cpp:392 now builds the drop-in
+    assert "readGpB200FromFile" in syms
