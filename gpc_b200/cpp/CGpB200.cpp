@@ -307,38 +307,6 @@ void CGpB200::out(CMatrix& yPred, CMatrix& probPred, const CMatrix& Xin) const
   (this->*memberOf(CGpNoiseTag()))->out(yPred, probPred, muTest, varSigmaTest); // CGp.cpp:459
 }
 
-void CGpB200::optimise(unsigned int iters)
-{
-  const char* e = getenv("GPC_NATIVE_SCG");
-  bool native = e && atoi(e) && getDefaultOptimiser() == SCG && !isOutputScaleLearnt() && onDevice();
-  if(native && getKernel()->priorLogProb() != 0.0)
-    native = false; // the native loop optimises the likelihood alone
-  if(!native)
-  {
-    CGp::optimise(iters);
-    return;
-  }
-  if(getVerbosity() > 2)
-  {
-    cout << "Initial model:" << endl;
-    display(cout);
-  }
-  upload();
-  int its = 0, evals = 0;
-  int rc = gpc_gp_optimise_scg(dev, bridge.compsWritable(), bridge.numComps(), (int)iters, getParamTol(), getObjectiveTol(),
-                               0, &its, &evals);
-  bridge.writeBack(const_cast<CKern*>(getKernel()));
-  setKupToDate(false);
-  state = STALE;
-  nEvals += (unsigned long)evals;
-  if(rc)
-    fail(rc);
-  if(getVerbosity() > 1)
-    cout << "... done. " << endl;
-  if(getVerbosity() > 0)
-    display(cout);
-}
-
 void CGpB200::download(int which, CMatrix& dst, bool square) const
 {
   if(!dev || state == STALE)

@@ -9,7 +9,8 @@
 // are re-bound to the C ABI of libgpc_b200.so (include/gpc_b200.h): K, LcholK, invK and Alpha live on the device in a
 // gpc_ctx owned by this object; one evaluation is ONE gpc_eval call (K build -> jitChol -> K^-1 -> alpha -> gradient,
 // one host synchronisation).  The non-virtual methods of the same path (posteriorMeanVar, posteriorMean, the two-output
-// out) are redeclared here so that code holding a CGpB200 uses the device too.
+// out) are redeclared here so that code holding a CGpB200 uses the device too.  CGp::optimise and every optimiser of
+// COptimisable (SCG, CG, GD, BFGS) are inherited as they are: they only see the virtuals.
 //
 // Anything outside the device path -- sparse approximations (DTC/FITC/PITC), kernel components the library does not
 // implement, optimiseX on a CGp -- falls through to the inherited host implementation, call by call.
@@ -41,10 +42,6 @@ class CGpB200 : public CGp
   void out(CMatrix& yPred, CMatrix& probPred, const CMatrix& inData) const;
   void posteriorMeanVar(CMatrix& mu, CMatrix& varSigma, const CMatrix& X) const;
   void posteriorMean(CMatrix& mu, const CMatrix& X) const;
-  // CGp::optimise (CGp.cpp:1537-1553).  With GPC_NATIVE_SCG=1 in the environment, the default SCG optimiser, no priors
-  // and fixed scales, the whole loop runs inside the library (gpc_gp_optimise_scg); otherwise the inherited optimisers
-  // drive the virtuals above.
-  void optimise(unsigned int iters = 1000);
 
   // the host copies of the state (for -DDBG style inspection): N x N each, filled from the device on request
   void downloadK(CMatrix& K) const { download(GPC_MAT_K, K, true); }

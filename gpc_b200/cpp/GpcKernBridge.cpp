@@ -100,9 +100,3 @@ void GpcKernBridge::finishGradient(const CKern* kern, double* g) const
     g[idx] *= kern->getTransformGradFact(kern->getParam(idx), i);
   }
 }
-
-void GpcKernBridge::writeBack(CKern* kern) const
-{
-  for(unsigned int i = 0; i < nTotal; i++)
-    kern->setParam(vals[i], i);
-}

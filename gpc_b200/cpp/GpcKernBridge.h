@@ -21,7 +21,6 @@ class GpcKernBridge
   bool sync(const CKern* kern, unsigned int inputDim);
   bool isSupported() const { return supported; }
   const gpc_kcomp* comps() const { return &kc[0]; }
-  gpc_kcomp* compsWritable() { return &kc[0]; }
   int numComps() const { return (int)kc.size(); }
   unsigned int getNumParams() const { return nTotal; }
   const std::vector<double>& naturalParams() const { return vals; }
@@ -29,8 +28,6 @@ class GpcKernBridge
   // Adds each component's prior gradient once (regularise=true on the first output only, CGp.cpp:1105-1112) and
   // multiplies by gradfact of the parameter's transform: the result is what CKern::getGradTransParams returns.
   void finishGradient(const CKern* kern, double* g) const;
-  // after the library optimised the parameters in place (gpc_gp_optimise_scg): write them back into the kernel object
-  void writeBack(CKern* kern) const;
 
  private:
   bool walk(const CKern* kern, unsigned int inputDim);
