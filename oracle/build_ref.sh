@@ -99,6 +99,11 @@ if [ -f "$SHIMDIR/libgpc_b200.so" ] && [ -d "$CPPDIR" ]; then
   g++ -o "$OUT/gp_l2" ../obj_l2/gp.o $L2 CGp.o CGplvm.o $COMMON $LNK
   g++ -o "$OUT/gplvm_l2" ../obj_l2/gplvm.o $L2 CGp.o CGplvm.o $COMMON $LNK
   g++ -o "$OUT/cgp_b200_check" ../obj_l2/cgp_b200_check.o $L2 CGp.o CGplvm.o $COMMON $LNK
+  # a host test double of libgpc_b200.so made of the reference's own classes (tests/cpp/mock_gpc_b200.cpp): lets the CPU
+  # tests drive the DEVICE-path logic of the C++ host classes without a GPU (LD_LIBRARY_PATH=oracle/_ref/mock)
+  mkdir -p "$OUT/mock"
+  g++ $CXXL -c "$HERE/../tests/cpp/mock_gpc_b200.cpp" -o "$OUT/obj_l2/mock_gpc_b200.o"
+  g++ -shared -o "$OUT/mock/libgpc_b200.so" "$OUT/obj_l2/mock_gpc_b200.o" $COMMON "$OB" -Wl,-rpath,"$SP" -lm
   echo "build_ref: built $OUT/gp_l2, gplvm_l2, cgp_b200_check (reference front-ends on CGpB200 / CGplvmB200)"
 fi
 echo "build_ref: built $OUT/libgpcref.so, gp, gplvm (OpenBLAS: $OB)"

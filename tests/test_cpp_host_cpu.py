@@ -136,3 +136,50 @@ def test_makefile_builds_the_host_classes_against_the_reference_tree(tmp_path):
     syms = subprocess.run(["nm", "-C", str(tmp_path / "gp_dropin.o")], capture_output=True, text=True).stdout
     assert "CGpB200::CGpB200(CKern*, CNoise*, CMatrix*, int, unsigned int, int)" in syms    # gp.cpp:392 now builds the drop-in
     assert "readGpB200FromFile" in syms
+
+
+# ---- the DEVICE-path logic of the C++ host classes, driven through a host test double of the library -------------------
+MOCK = os.path.join(ROOT, "oracle", "_ref", "mock")
+
+
+def _run_mock(*args):
+    """cgp_b200_check with tests/cpp/mock_gpc_b200.cpp (the C ABI implemented with the reference's own classes) placed in
+    front of libgpc_b200.so: uploads, caching, gradient assembly and error mapping of CGpB200 / CGplvmB200 run without a
+    GPU.  What it cannot show is the device arithmetic -- that is tests/test_gpu_cpp_host.py."""
+    if not (os.path.exists(CHECK) and os.path.exists(os.path.join(MOCK, "libgpc_b200.so"))):
+        pytest.skip("oracle/_ref/cgp_b200_check or the mock library not built")
+    env = dict(os.environ, LD_LIBRARY_PATH=MOCK + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([CHECK] + [str(a) for a in args], capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "mock_gpc_b200: host test double in use" in out.stderr
+    lines = [l for l in out.stdout.splitlines() if not l.startswith("Warning:")]
+    return json.loads("\n".join(lines))
+
+
+def _rel(a, b):
+    import numpy as np
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1.0)))
+
+
+@pytest.mark.parametrize("mode,N,D,d,kern,scale,prior,iters", [
+    ("gp", 40, 1, 1, "rbf,bias,white", 0, 0, 15),
+    ("gp", 90, 3, 1, "rbf,lin,bias,white", 0, 0, 12),
+    ("gp", 80, 4, 2, "rbfard,bias,white", 0, 0, 12),
+    ("gp", 70, 2, 1, "rbf,white", 1, 0, 12),            # learnt output scale: m keeps its old scale (CGp.cpp:429-437)
+    ("gp", 60, 3, 1, "matern52,poly,white", 0, 1, 12),  # a gamma prior on the first parameter
+    ("gplvm", 50, 2, 5, "rbf,bias,white", 0, 0, 8),
+    ("gplvm", 45, 3, 4, "rbfard,white", 1, 0, 0),
+    ("gplvm", 40, 2, 6, "matern52,lin,white", 1, 1, 6),
+])
+def test_device_path_logic_of_the_host_classes_through_the_test_double(mode, N, D, d, kern, scale, prior, iters):
+    r = _run_mock(mode, N, D, d, 7, kern, scale, prior, iters)
+    assert r["on_device"] == 1
+    assert r["evals_first"] == 1          # gradient + two likelihood calls at one point: ONE evaluation
+    assert r["ll_dev"] == r["ll_dev_again"]
+    assert _rel(r["ll_ref"], r["ll_dev"]) <= 1e-10
+    assert _rel(r["g_ref"], r["g_dev"]) <= 1e-8
+    assert _rel(r["out_ref"], r["out_dev"]) <= 1e-9 and _rel(r["std_ref"], r["std_dev"]) <= 1e-9
+    if iters:
+        assert r["opt_ll_ref"] > r["ll_ref"] and r["device_evals"] > iters
+        assert _rel(r["opt_ref"], r["opt_dev"]) <= 1e-5 and _rel(r["opt_ll_ref"], r["opt_ll_dev"]) <= 1e-6
