@@ -8,6 +8,7 @@
 //   cgp_b200_check gp    N D d seed kern1,kern2,... [scale] [prior] [iters]
 //   cgp_b200_check gplvm N q d seed kern1,kern2,... [scale] [prior] [iters]
 //   cgp_b200_check bridge N D 0 seed kern1,kern2,... 0 [prior]   GpcKernBridge alone (host only)
+//   cgp_b200_check download N D d seed kern1,kern2,...                      CGpB200::downloadK/InvK/LcholK/Alpha through identities
 //   cgp_b200_check sparse N D d seed kern1,kern2,... approx M beta           the REFERENCE's DTC(1) / FITC(2) / DTCVAR(4) ll + gradient
 //   cgp_b200_check modelwrite N D d seed kern1,kern2,... scale prior path   the REFERENCE writes a gp model file (CGp.cpp:1640-1666)
 //   cgp_b200_check modelread 0 0 0 0 path                                   the REFERENCE reads one and prints what it holds
@@ -17,6 +18,7 @@
 //                                                           bench.py, driven the way COptimisable drives a model)
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cmath>
 #include <ctime>
 #include <string>
@@ -294,6 +296,70 @@ static int runBridge(unsigned int N, unsigned int D, const std::string& spec, bo
   }
   printVec("g_ref", gTrans, true);
   printf("}\n");
+  return 0;
+}
+
+// CGpB200::downloadK / downloadInvK / downloadLcholK / downloadAlpha: the device-resident state back in CMatrix form
+// (what -DDBG exposes of the reference's K, invK, LcholK, Alpha, CGp.h:359-361), checked through identities
+static int runDownload(unsigned int N, unsigned int D, unsigned int d, const std::string& spec)
+{
+  CMatrix X(N, D), y(N, d);
+  for(unsigned int j = 0; j < D; j++)
+    for(unsigned int i = 0; i < N; i++)
+      X.setVal(normal01(), i, j);
+  for(unsigned int j = 0; j < d; j++)
+    for(unsigned int i = 0; i < N; i++)
+      y.setVal(sin(X.getVal(i, 0) + 0.5 * j) + 0.1 * normal01(), i, j);
+  CCmpndKern kern(X);
+  buildKernel(kern, spec, D, false);
+  CGaussianNoise noise(&y);
+  CGpB200 dev(&kern, &noise, &X, CGp::FTC, 0, 0);
+  bool threw = false;
+  CMatrix K, Kinv, L, A;
+  try
+  {
+    dev.downloadK(K); // nothing evaluated yet: must refuse
+  }
+  catch(ndlexceptions::Error&)
+  {
+    threw = true;
+  }
+  CMatrix g(1, dev.getOptNumParams());
+  dev.logLikelihoodGradient(g);
+  dev.downloadK(K);
+  dev.downloadInvK(Kinv);
+  dev.downloadLcholK(L);
+  dev.downloadAlpha(A);
+  double eK = 0.0, eI = 0.0, eL = 0.0, eA = 0.0, eU = 0.0;
+  for(unsigned int i = 0; i < N; i++)
+    for(unsigned int j = 0; j < N; j++)
+    {
+      double kref = (i == j) ? kern.diagComputeElement(X, i) : kern.computeElement(X, i, X, j);
+      eK = std::max(eK, fabs(K.getVal(i, j) - kref));
+      double s = 0.0, l = 0.0;
+      for(unsigned int k = 0; k < N; k++)
+      {
+        s += K.getVal(i, k) * Kinv.getVal(k, j);
+        l += L.getVal(i, k) * L.getVal(j, k);
+      }
+      eI = std::max(eI, fabs(s - (i == j ? 1.0 : 0.0)));
+      eL = std::max(eL, fabs(l - K.getVal(i, j)));
+      if(j > i)
+        eU = std::max(eU, fabs(L.getVal(i, j))); // LcholK is lower with a zero strict upper triangle (CGp.cpp:890)
+    }
+  for(unsigned int j = 0; j < d; j++)
+    for(unsigned int i = 0; i < N; i++)
+    {
+      double s = 0.0;
+      for(unsigned int k = 0; k < N; k++)
+        s += Kinv.getVal(i, k) * (y.getVal(k, j) - dev.getBiasVal(j)) / dev.getScaleVal(j);
+      eA = std::max(eA, fabs(s - A.getVal(i, j)));
+    }
+  printf("{\"mode\": \"download\", \"refused_before_eval\": %d, \"rows\": [%u, %u, %u, %u], \"cols\": [%u, %u, %u, %u], "
+         "\"symmetric_flags\": [%d, %d, %d], \"err_K\": %.3g, \"err_KinvK\": %.3g, \"err_LLt\": %.3g, \"err_upper\": %.3g, "
+         "\"err_alpha\": %.3g}\n",
+         threw ? 1 : 0, K.getRows(), Kinv.getRows(), L.getRows(), A.getRows(), K.getCols(), Kinv.getCols(), L.getCols(),
+         A.getCols(), K.isSymmetric() ? 1 : 0, Kinv.isSymmetric() ? 1 : 0, L.isSymmetric() ? 1 : 0, eK, eI, eL, eU, eA);
   return 0;
 }
 
@@ -582,6 +648,8 @@ int main(int argc, char** argv)
       return runGp(N, D, d, spec, scale, prior, iters);
     if(mode == "gplvm")
       return runGplvm(N, D, d, spec, scale, prior, iters);
+    if(mode == "download")
+      return runDownload(N, D, d, spec);
     if(mode == "sparse") // sparse N D d seed kernels approx(1 dtc, 2 fitc, 4 dtcvar) M beta
       return runSparse(N, D, d, spec, argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 10, argc > 9 ? atof(argv[9]) : 10.0);
     if(mode == "modelwrite")

@@ -183,3 +183,19 @@ def test_device_path_logic_of_the_host_classes_through_the_test_double(mode, N, 
     if iters:
         assert r["opt_ll_ref"] > r["ll_ref"] and r["device_evals"] > iters
         assert _rel(r["opt_ref"], r["opt_dev"]) <= 1e-5 and _rel(r["opt_ll_ref"], r["opt_ll_dev"]) <= 1e-6
+
+
+def test_download_accessors_of_cgp_b200_through_the_test_double():
+    """CGpB200::downloadK / downloadInvK / downloadLcholK / downloadAlpha (the -DDBG view of CGp.h:359-361): refused before
+    anything was evaluated, right shapes and symmetry flags, and the identities K K^-1 = I, L L' = K, alpha = K^-1 m."""
+    if not (os.path.exists(CHECK) and os.path.exists(os.path.join(MOCK, "libgpc_b200.so"))):
+        pytest.skip("oracle/_ref/cgp_b200_check or the mock library not built")
+    env = dict(os.environ, LD_LIBRARY_PATH=MOCK + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([CHECK, "download", "50", "3", "2", "5", "rbf,lin,bias,white"], capture_output=True, text=True,
+                         timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-1500:]
+    r = json.loads(out.stdout)
+    assert r["refused_before_eval"] == 1
+    assert r["rows"] == [50, 50, 50, 50] and r["cols"] == [50, 50, 50, 2] and r["symmetric_flags"] == [1, 1, 0]
+    assert r["err_K"] <= 1e-12 and r["err_KinvK"] <= 1e-10 and r["err_LLt"] <= 1e-12 and r["err_alpha"] <= 1e-10
+    assert r["err_upper"] == 0.0

@@ -164,3 +164,18 @@ def test_unmodified_gp_front_end_gnuplot_on_cgp_b200(tmp_path):
         b = np.loadtxt(str(tmp_path / ("plot_l2_%s.dat" % part)))
         assert a.shape == b.shape and a.size > 0
         assert _rel(a, b) <= tol, part
+
+
+def test_download_accessors_of_cgp_b200():
+    """CGpB200::downloadK / downloadInvK / downloadLcholK / downloadAlpha on the device-resident state: K against the
+    reference's computeElement / diagComputeElement, K K^-1 = I, L L' = K with a zero strict upper triangle, alpha = K^-1 m."""
+    if not os.path.exists(CHECK):
+        pytest.skip("oracle/_ref/cgp_b200_check not built")
+    out = subprocess.run([CHECK, "download", "300", "3", "2", "5", "rbf,lin,bias,white"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-1500:]
+    r = json.loads(out.stdout)
+    assert r["refused_before_eval"] == 1
+    assert r["rows"] == [300] * 4 and r["cols"] == [300, 300, 300, 2] and r["symmetric_flags"] == [1, 1, 0]
+    assert r["err_K"] <= 1e-12 and r["err_KinvK"] <= 1e-8 and r["err_LLt"] <= 1e-10 and r["err_alpha"] <= 1e-8
+    assert r["err_upper"] == 0.0
