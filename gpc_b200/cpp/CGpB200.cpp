@@ -338,7 +338,7 @@ CGpB200* readGpB200FromFile(const string modelFileName, int verbosity)
   {
     pmodel = readGpB200FromStream(in);
   }
-  catch(ndlexceptions::StreamFormatError err)
+  catch(ndlexceptions::StreamFormatError& err)
   {
     throw ndlexceptions::FileFormatError(modelFileName, err);
   }

@@ -213,7 +213,7 @@ CGplvmB200* readGplvmB200FromFile(const string modelFileName, const int verbosit
   {
     pmodel = readGplvmB200FromStream(in);
   }
-  catch(ndlexceptions::FileFormatError err)
+  catch(ndlexceptions::FileFormatError& err)
   {
     throw ndlexceptions::FileFormatError(modelFileName);
   }
