@@ -120,3 +120,33 @@ def sparse_loglik_grad(kern, X, y, Xu, beta, approx="dtc", bias=None, scale=None
     glogbeta = gbeta * beta                 # exp transform of beta (CGp.cpp:1073-1076, CTransform.cpp:25-53)
     g = np.concatenate([gXu.T.reshape(-1), gk, [glogbeta]])
     return dict(ll=ll, g=g, gXu=gXu, gk=gk, gbeta=glogbeta)
+
+
+def sparse_posterior(kern, X, y, Xu, beta, Xs, approx="dtc", bias=None, scale=None):
+    """CGp::posteriorMeanVar for the sparse approximations: updateAlpha (CGp.cpp:490-521) and the sparse branch of
+    _posteriorVar (CGp.cpp:584-599), then output scale and bias (CGp.cpp:561-573, 618-626).  With Lambda as above and
+    A = K_uu + K_uf Lambda^-1 K_fu (beta times the reference's A):
+        mean = k_*u' A^-1 K_uf Lambda^-1 m,      var = k_** - k_*u' (K_uu^-1 - A^-1) k_*u + 1/beta
+    (k_** through diagComputeElement, i.e. with the white noise; the 1/beta is added for every approximation;
+    DTCVAR predicts like DTC)."""
+    X = np.asarray(X, dtype=np.float64)
+    Xu = np.asarray(Xu, dtype=np.float64)
+    Xs = np.asarray(Xs, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(X.shape[0], -1)
+    N, d = y.shape
+    bias = np.zeros(d) if bias is None else np.asarray(bias, dtype=np.float64).reshape(d)
+    scale = np.ones(d) if scale is None else np.asarray(scale, dtype=np.float64).reshape(d)
+    m = (y - bias[None, :]) / scale[None, :]
+    Kuu = O.kern_compute(kern, Xu)
+    Kuf = O.kern_cross(kern, Xu, X)
+    lam = np.full(N, 1.0 / beta)
+    if approx.lower() == "fitc":
+        lam = lam + (O.kern_diag(kern, X) - np.einsum("ij,ij->j", Kuf, np.linalg.solve(Kuu, Kuf)))
+    KufL = Kuf / lam[None, :]
+    A = Kuu + KufL @ Kuf.T
+    A = 0.5 * (A + A.T)
+    alpha = np.linalg.solve(A, KufL @ m)                 # M x d
+    ksu = O.kern_cross(kern, Xu, Xs)                     # M x Ns
+    mu = ksu.T @ alpha
+    v = O.kern_diag(kern, Xs) - np.einsum("ij,ij->j", ksu, np.linalg.solve(Kuu, ksu) - np.linalg.solve(A, ksu)) + 1.0 / beta
+    return mu * scale[None, :] + bias[None, :], v[:, None] * (scale * scale)[None, :]

@@ -400,6 +400,16 @@ static int runSparse(unsigned int N, unsigned int D, unsigned int d, const std::
   printVec("bias", bias);
   printVec("X_u", model.X_u);
   printVec("params", p);
+  // prediction through the sparse branches of updateAlpha / _posteriorVar (CGp.cpp:469-534, 600-627)
+  const unsigned int Ns = 7;
+  CMatrix Xs(Ns, D), mu(Ns, d), var(Ns, d);
+  for(unsigned int j = 0; j < D; j++)
+    for(unsigned int i = 0; i < Ns; i++)
+      Xs.setVal(1.2 * normal01(), i, j);
+  model.posteriorMeanVar(mu, var, Xs);
+  printVec("Xs", Xs);
+  printVec("mu", mu);
+  printVec("var", var);
   printVec("g", g, true);
   printf("}\n");
   return 0;

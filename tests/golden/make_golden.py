@@ -197,7 +197,9 @@ def sparse_fixtures():
         out.update({tag + "_X": np.array(r["X"]).reshape(D, N).T, tag + "_y": np.array(r["y"]).reshape(d, N).T,
                     tag + "_Xu": np.array(r["X_u"]).reshape(D, M).T, tag + "_beta": r["beta"], tag + "_bias": np.array(r["bias"]),
                     tag + "_params": np.array(r["params"]), tag + "_grads": np.array(r["g"]), tag + "_ll": r["ll"],
-                    tag + "_approx": np.array(r["approx"]), tag + "_types": np.array(spec.split(","))})
+                    tag + "_approx": np.array(r["approx"]), tag + "_types": np.array(spec.split(",")),
+                    tag + "_Xs": np.array(r["Xs"]).reshape(D, -1).T, tag + "_mu": np.array(r["mu"]).reshape(d, -1).T,
+                    tag + "_var": np.array(r["var"]).reshape(d, -1).T})
     np.savez_compressed(os.path.join(HERE, "sparse_reference.npz"), **out)
 
 

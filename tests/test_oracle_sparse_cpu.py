@@ -59,6 +59,20 @@ def test_sparse_oracle_against_the_compiled_reference(ref, tag):
     assert np.max(np.abs(r["g"] - g) / np.maximum(1.0, np.abs(g))) <= 1e-8
 
 
+@pytest.mark.parametrize("tag", SPARSE_TAGS)
+def test_sparse_posterior_against_the_compiled_reference(ref, tag):
+    """CGp::posteriorMeanVar through the sparse branches of updateAlpha / _posteriorVar (CGp.cpp:490-521, 584-599)."""
+    X, y, Xu = ref[tag + "_X"], ref[tag + "_y"], ref[tag + "_Xu"]
+    D, M = X.shape[1], Xu.shape[0]
+    types = [str(t) for t in ref[tag + "_types"]]
+    P = sum(O.nparams(t, D) for t in types)
+    kern = O.kern_from_trans(types, ref[tag + "_params"][M * D:M * D + P], D)
+    mu, var = S.sparse_posterior(kern, X, y, Xu, float(ref[tag + "_beta"]), ref[tag + "_Xs"], str(ref[tag + "_approx"]),
+                                 bias=np.ravel(ref[tag + "_bias"]))
+    assert np.max(np.abs(mu - ref[tag + "_mu"]) / np.maximum(1.0, np.abs(ref[tag + "_mu"]))) <= 1e-8
+    assert np.max(np.abs(var - ref[tag + "_var"]) / np.maximum(1.0, np.abs(ref[tag + "_var"]))) <= 1e-8
+
+
 def test_sparse_gradient_is_the_derivative_of_the_likelihood(ref):
     """independent of any fixture: central differences along random directions, every approximation"""
     tag = "fitc_rbf"
