@@ -114,6 +114,30 @@ class ClockSampler:
         return out
 
 
+def m2_summary(N, phases, hbm_gbs, bf16_tflops, dmma_peak_tflops, slices):
+    """BASELINE.json's second metric, "potrf + K-build GF/s vs fp64 roofline" (SURVEY.md 8(d) M2), from the phase timings
+    of one evaluation: potrf counted as N^3/3 flops against (a) the fp64 DMMA pipe measured on this GPU and (b) the
+    fp64-equivalent peak of the int8 tensor pipe the large products run on; K build as 8 N^2/2 bytes written against the
+    measured HBM copy bandwidth.  Pure arithmetic on numbers the bench already has; never raises."""
+    out = {}
+    try:
+        pt = float(phases["potrf"]) * 1e-3
+        kb = float(phases["kbuild"]) * 1e-3
+        tf = (float(N) ** 3 / 3.0) / pt / 1e12 if pt > 0 else None
+        gbs = 8.0 * float(N) ** 2 / 2.0 / kb / 1e9 if kb > 0 else None
+        int8_equiv = 2.0 * float(bf16_tflops) / (slices * (slices + 1) / 2.0) if slices else None
+        out = {"potrf_tflops": tf, "potrf_gflops": tf * 1e3 if tf is not None else None,
+               "potrf_frac_of_dmma_peak": tf / dmma_peak_tflops if tf and dmma_peak_tflops else None,
+               "potrf_frac_of_int8_equiv_peak": tf / int8_equiv if tf and int8_equiv else None,
+               "potrf_note": "potrf phase = factor + the triangular inverse built alongside it (1.25 N^3/3 executed flops, "
+                             "DESIGN.md 4.3); the fraction counts only the N^3/3 of dpotrf_",
+               "kbuild_gbs": gbs, "kbuild_frac_of_hbm": gbs / float(hbm_gbs) if gbs and hbm_gbs else None,
+               "peaks": {"dmma_tflops": dmma_peak_tflops, "int8_equiv_fp64_tflops": int8_equiv, "hbm_gbs": hbm_gbs}}
+    except Exception as e:  # the headline line must never be lost to this
+        out = {"error": str(e)}
+    return out
+
+
 def reference_arm(args, rank, world):
     """--impl reference: the UNMODIFIED reference's CPU path (oracle/_ref = GPc compiled from /root/reference,
     OpenBLAS on all host threads) on the same workload.  Rank 0 only."""
@@ -413,6 +437,7 @@ def main():
             "phases_ms": phases, "ll": ll,
             "potrf_tflops": (N ** 3 / 3) / (phases["potrf"] * 1e-3) / 1e12,
             "kbuild_gbs": 8.0 * N * N / 2 / (phases["kbuild"] * 1e-3) / 1e9,
+            "m2": m2_summary(N, phases, mp.get("hbm_gbs"), bf16, peak.value, S),
             "also": also,
         }
         print(json.dumps(line))
