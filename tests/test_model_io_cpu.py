@@ -206,3 +206,28 @@ def test_gplvm_model_files_the_library_does_not_take(tmp_path):
     with pytest.raises(GpcError):                                          # a gp file is not a gplvm file
         _driver("modelwrite", 25, 2, 1, 5, "rbf,white", 0, 0, ref_file)
         io.read_gplvm_model(ref_file)
+
+
+def test_model_from_gp_writes_what_the_reference_reads(tmp_path):
+    """gpc_b200.CGp.writeModelFile = io.model_from_gp + write_gp_model.  The CGp object itself needs a GPU; its host-side
+    attributes are all that model_from_gp touches, so a stand-in with the same attributes is enough here.  The reference
+    must read the kernel, scale, bias and Gaussian noise (bias = column means of y, variance 1e-6) back exactly."""
+    import types as _types
+    import gpc_b200 as G
+    rng = np.random.default_rng(4)
+    X, y = rng.standard_normal((30, 3)), rng.standard_normal((30, 2))
+    kern = G.make_kern(["rbfard", "poly", "bias", "white"], 3, [0.1, -0.2, 0.3, -0.4, 0.5, 0.2, -0.1, 0.05, -1.0, -2.0])
+    kern._components()[1].setDegree(3.0)
+    gp = _types.SimpleNamespace(pkern=kern, X=X, y=y, scale=np.array([1.5, 0.7]), bias=np.array([0.3, -1.25]),
+                                getNumData=lambda: 30, getOutputDim=lambda: 2)
+    path = str(tmp_path / "m.model")
+    io.write_gp_model(path, io.model_from_gp(gp), "from the Python mirror")
+    seen = _driver("modelread", 0, 0, 0, 0, path)
+    assert seen["num_data"] == 30 and seen["input_dim"] == 3 and seen["output_dim"] == 2
+    assert seen["scale"] == [1.5, 0.7] and seen["bias"] == [0.3, -1.25]
+    assert seen["types"] == [CODE[t] for t in ("rbfard", "poly", "bias", "white")]
+    assert seen["kern_params"] == list(kern.params) and seen["degree"][1] == 3.0
+    assert seen["noise_type"] == "gaussian" and seen["noise_params"] == list(y.mean(axis=0)) + [1e-6]
+    back = io.read_gp_model(path)
+    k2 = io.kern_from_model(back)
+    assert list(k2.params) == list(kern.params) and k2._components()[1].getDegree() == 3.0
