@@ -272,6 +272,13 @@ def main():
         sampler.start()
     ms_dev, launches = timed(args.steps, False, 100)
     phases = ctx.last_timings()
+    enqueue_ms = None   # host time the last evaluation spent queueing its launches before its single synchronisation
+    try:
+        _enq = C.c_double(0.0)
+        if lib().gpc_last_enqueue_ms(ctx.handle, C.byref(_enq)) == 0:
+            enqueue_ms = float(_enq.value)
+    except Exception:
+        enqueue_ms = None
     ms_e2e, _ = timed(args.steps, True, 200)
     clocks = sampler.stop() if rank == 0 else {}
     ll = -0.5 * (out[1] + out[0]) - N * 0.5 * np.log(2 * np.pi)
@@ -434,7 +441,7 @@ def main():
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "evals/s",
                     "h2d_bytes_per_step": int(8 * N * D + 8 * N), "d2h_bytes_per_step": int(8 * (8 + P) + 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "phases_ms": phases, "ll": ll,
+            "phases_ms": phases, "host_enqueue_ms": enqueue_ms, "ll": ll,
             "potrf_tflops": (N ** 3 / 3) / (phases["potrf"] * 1e-3) / 1e12,
             "kbuild_gbs": 8.0 * N * N / 2 / (phases["kbuild"] * 1e-3) / 1e9,
             "m2": m2_summary(N, phases, mp.get("hbm_gbs"), bf16, peak.value, S),
