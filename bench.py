@@ -36,6 +36,8 @@ WORKLOADS = {
     "c2": dict(N=8192, D=8, types=["rbf", "white"], desc="C2 synthetic N=8192 D=8 rbf(gamma=1/8,var=1)+white(0.01), d=1"),
     "c3": dict(N=32768, D=16, types=["rbfard", "white"],
                desc="C3 synthetic N=32768 D=16 rbfard(gamma=1/16,var=1,s_k=0.25+0.5k/15)+white(0.01), d=1"),
+    "c4": dict(N=65536, D=32, types=["matern52", "white"],
+               desc="C4 synthetic N=65536 D=32 matern52(l=sqrt(32),var=1)+white(0.01), d=1"),
 }
 
 
@@ -49,6 +51,8 @@ def make_inputs(name):
     y = np.asfortranarray(y - y.mean())
     if name == "c2":
         params = np.array([1.0 / D, 1.0, 0.01])
+    elif name == "c4":
+        params = np.array([np.sqrt(float(D)), 1.0, 0.01])
     else:
         params = np.concatenate([[1.0 / D, 1.0], 0.25 + 0.5 * np.arange(D) / (D - 1), [0.01]])
     return X, y, params

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpc_b200.so")
 SHIM = os.path.join(HERE, "libgpc_lapack_shim.so")
-SOURCES = ["dense.cu", "ozaki.cu", "gpkern.cu", "api.cu", "lapack_api.cu", "api_dev.cu", "host.cu", "modelio.cu"]
+SOURCES = ["dense.cu", "ozaki.cu", "gpkern.cu", "api.cu", "lapack_api.cu", "host.cu", "modelio.cu", "dist.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "gpc_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or procs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"]
         subprocess.check_call(cmd)
     # the Fortran-ABI shim (dpotrf_, dpotri_, dtrsm_, dsyrk_, dgemm_ -> gpc_d*): link or LD_PRELOAD it in front of a
     # BLAS and the unmodified reference objects run those calls on the GPU (level 0)

@@ -375,14 +375,18 @@ static Dense dense_of(gpc_ctx* c) {
 }
 
 static int ensure_inverse_buffers(gpc_ctx* c) {
-  if (c->Kinv) return GPC_OK;
+  // each buffer is checked on its own: a call that ran out of memory half-way is completed (or fails again) next time
   size_t nn = (size_t)c->Npmax * c->Npmax;
   // K^-1 also serves as scratch of potrf_inv_rec: tmpL ((Np/2+TILE)^2) + Tpool (<= Np^2/3 + slack)
   size_t scratch = (size_t)(c->Npmax / 2 + TILE) * (size_t)(c->Npmax / 2 + TILE) + 2 * (potrf_inv_tspace(c->Npmax) + 16);
-  GPC_CUDA_CHECK(cudaMalloc(&c->Kinv, (nn > scratch ? nn : scratch) * sizeof(double)));
-  if (c->use_winv) GPC_CUDA_CHECK(cudaMalloc(&c->Winv, nn * sizeof(double)));
-  if (!c->use_winv) GPC_CUDA_CHECK(cudaMalloc(&c->W, (potri_workspace(c->Npmax) + 16) * sizeof(double)));
-  GPC_CUDA_CHECK(cudaMalloc(&c->symm_part, (size_t)symm_chunks(c->Npmax) * 4 * c->Npmax * sizeof(double)));
+  if (!c->Kinv) GPC_CUDA_CHECK(cudaMalloc(&c->Kinv, (nn > scratch ? nn : scratch) * sizeof(double)));
+  if (c->use_winv && !c->Winv) {
+    GPC_CUDA_CHECK(cudaMalloc(&c->Winv, nn * sizeof(double)));
+    c->winv_np = 0;
+  }
+  if (!c->use_winv && !c->W) GPC_CUDA_CHECK(cudaMalloc(&c->W, (potri_workspace(c->Npmax) + 16) * sizeof(double)));
+  if (!c->symm_part)
+    GPC_CUDA_CHECK(cudaMalloc(&c->symm_part, (size_t)symm_chunks(c->Npmax) * 4 * c->Npmax * sizeof(double)));
   return GPC_OK;
 }
 
@@ -445,6 +449,8 @@ double gpc_transform_gradfact(int tr, double x) {
   return 1.0;
 }
 
+static int ctx_create_impl(gpc_ctx* c, int device, int64_t Nmax, int Dmax, int dout_max, const cudaDeviceProp& prop);
+
 int gpc_ctx_create(gpc_ctx** out, int device, int64_t Nmax, int Dmax, int dout_max) {
   if (!out || Nmax < 1 || Dmax < 1 || dout_max < 1) {
     set_error("gpc_ctx_create: bad arguments");
@@ -465,6 +471,20 @@ int gpc_ctx_create(gpc_ctx** out, int device, int64_t Nmax, int Dmax, int dout_m
   }
   gpc_ctx* c = new gpc_ctx();
   memset(c, 0, sizeof(*c));
+  *out = nullptr;
+  int rc = ctx_create_impl(c, device, Nmax, Dmax, dout_max, prop);
+  if (rc != GPC_OK) {  // e.g. out of memory at large N: give back what was allocated (the destroy tolerates null members)
+    std::string keep = g_error;
+    gpc_ctx_destroy(c);
+    cudaGetLastError();
+    g_error = keep;
+    return rc;
+  }
+  *out = c;
+  return GPC_OK;
+}
+
+static int ctx_create_impl(gpc_ctx* c, int device, int64_t Nmax, int Dmax, int dout_max, const cudaDeviceProp& prop) {
   c->device = device;
   c->Nmax = Nmax;
   c->Npmax = round_up(Nmax, TILE);
@@ -503,7 +523,6 @@ int gpc_ctx_create(gpc_ctx** out, int device, int64_t Nmax, int Dmax, int dout_m
     for (auto& st : c->fork->side) GPC_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto& e : c->fork->ev) GPC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  *out = c;
   return GPC_OK;
 }
 
@@ -517,12 +536,15 @@ int gpc_ctx_destroy(gpc_ctx* c) {
   cudaFreeHost(c->hres); cudaFreeHost(c->hinfo);
   gpc_ctx_set_profile(c, 0);
   if (c->fork) {
-    for (auto st : c->fork->side) cudaStreamDestroy(st);
-    for (auto e : c->fork->ev) cudaEventDestroy(e);
+    for (auto st : c->fork->side)
+      if (st) cudaStreamDestroy(st);
+    for (auto e : c->fork->ev)
+      if (e) cudaEventDestroy(e);
     delete c->fork;
   }
-  for (int i = 0; i < 6; i++) cudaEventDestroy(c->ev[i]);
-  cudaStreamDestroy(c->own_stream);
+  for (int i = 0; i < 6; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return GPC_OK;
 }
@@ -560,8 +582,13 @@ int gpc_set_X(gpc_ctx* c, const double* X, int64_t N, int D, int64_t ldx) {
   }
   GPC_CUDA_CHECK(cudaSetDevice(c->device));
   int64_t Np = round_up(N, TILE);
-  if (c->haveX && (Np != c->Np || N != c->N))  // stale rows beyond the new N must read as zero
+  if (c->haveX && (Np != c->Np || N != c->N)) {  // stale rows beyond the new N must read as zero
     GPC_CUDA_CHECK(cudaMemsetAsync(c->X, 0, (size_t)c->Npmax * c->Dmax * sizeof(double), c->stream));
+    // m and alpha are laid out with the old leading dimension / row count: the caller has to set m again
+    GPC_CUDA_CHECK(cudaMemsetAsync(c->M, 0, (size_t)c->Npmax * c->dmax * sizeof(double), c->stream));
+    GPC_CUDA_CHECK(cudaMemsetAsync(c->alpha, 0, (size_t)c->Npmax * c->dmax * sizeof(double), c->stream));
+    c->haveM = false;
+  }
   c->N = N;
   c->Np = Np;
   c->D = D;
@@ -671,6 +698,7 @@ static int inverse_async(gpc_ctx* c) {
 
 int gpc_potrf(gpc_ctx* c, int* info, double* logdet) {
   GPC_CHECK(need(c, c && c->haveK, "gpc_potrf needs K"));
+  c->haveL = c->haveInv = c->haveAlpha = false;  // L is overwritten: valid again only if info == 0
   GPC_CHECK(potrf_async(c));
   GPC_CUDA_CHECK(cudaMemcpyAsync(c->hinfo, c->info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -764,7 +792,7 @@ static int ensure_tmp(gpc_ctx* c, int64_t elems) {
   cudaFree(c->tmp1);
   cudaFree(c->tmp2);
   c->tmp1 = c->tmp2 = nullptr;
-  c->tmp_cap = 0;
+  c->tmp_cap = 0;  // stays 0 if the second allocation fails: the pair is re-allocated by the next call
   GPC_CUDA_CHECK(cudaMalloc(&c->tmp1, (size_t)elems * sizeof(double)));
   GPC_CUDA_CHECK(cudaMalloc(&c->tmp2, (size_t)elems * sizeof(double)));
   c->tmp_cap = elems;
@@ -864,6 +892,7 @@ static int ensure_cross(gpc_ctx* c, int64_t Nsp) {
   if (c->Xs_cap < Nsp * c->Dmax) {
     cudaFree(c->Xs);
     c->Xs = nullptr;
+    c->Xs_cap = 0;
     GPC_CUDA_CHECK(cudaMalloc(&c->Xs, (size_t)Nsp * c->Dmax * sizeof(double)));
     c->Xs_cap = Nsp * c->Dmax;
   }
@@ -871,6 +900,7 @@ static int ensure_cross(gpc_ctx* c, int64_t Nsp) {
     cudaFree(c->Kc);
     cudaFree(c->Kc2);
     c->Kc = c->Kc2 = nullptr;
+    c->Kc_cap = 0;
     GPC_CUDA_CHECK(cudaMalloc(&c->Kc, (size_t)Nsp * c->Np * sizeof(double)));
     if (c->use_winv) GPC_CUDA_CHECK(cudaMalloc(&c->Kc2, (size_t)Nsp * c->Np * sizeof(double)));
     c->Kc_cap = Nsp * c->Np;
@@ -971,6 +1001,8 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
   bool wantX = (flags & 1) && gX;
   Dense d = dense_of(c);
   cudaStream_t s = c->stream;
+  // L, W, K^-1 and alpha are overwritten from here on: they only become valid again on the success path
+  c->haveL = c->haveInv = c->haveAlpha = false;
   const auto host_t0 = std::chrono::steady_clock::now();
   GPC_CUDA_CHECK(cudaEventRecord(c->ev[0], s));
   GPC_CHECK(launch_kbuild(ks, c->X, c->Np, c->N, c->Np, c->K, c->Np, s, &c->launches));

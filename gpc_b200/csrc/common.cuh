@@ -76,6 +76,20 @@ bool oz_wants(const GemmCall& g);
 int oz_slices();                  // configured number of slices  // true when launch_gemm should route this call to launch_gemm_ozaki
 int launch_gemm_ozaki(const GemmCall& g, cudaStream_t s, int64_t* launches, int slices = 0);  // 0: configured
 void oz_release_device(int dev);   // frees the per-device slice workspace
+// ---- block-cyclic one-sweep mode (dist.cu): panels pre-sliced into "slots", staircase update of the local matrix ----
+struct OzCycMaps {   // the two tensor maps (A: 128-row boxes, B: 64-row boxes) over one slot buffer
+  alignas(64) unsigned char opaque[2 * 128 + 128];
+  const uint8_t* slots;
+  int nb, S;
+};
+struct OzCycGrid { int P, Q, p, q; };
+size_t oz_slot_bytes(int nb, int S);   // bytes of one slot: S planes of nb x nb int8 + nb row scales
+int oz_slice_to_slots(const double* g, int64_t ld, bool kc, int64_t R, int nb, int S, int* emax_scratch, uint8_t* slots,
+                      int slot0, int slot_stride, cudaStream_t s, int64_t* launches);
+int oz_cyc_maps(OzCycMaps* out, const uint8_t* slots, int nslots, int nb, int S);
+int launch_oz_cyc_update(const OzCycMaps& maps, const OzCycGrid& gr, int kstep, int skip_i, int skip_j, double* C,
+                         int64_t ldc, int64_t r0, int64_t m, int64_t c0, int64_t n, int* errflag, cudaStream_t s,
+                         int64_t* launches);
 
 // potrf of one TILE x TILE diagonal block, in place (lower); also writes the inverse of the factor into
 // Dinv (TILE x TILE, ld TILE, upper part zero), adds 2*sum(log diag) to *logdet and records the first
@@ -165,6 +179,16 @@ int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* O
 size_t potri_workspace(int64_t n);  // doubles needed by potri_rec for an n x n factor
 
 // ---- GP layer (gpkern.cu) -----------------------------------------------------------------------------
+// local part of a block-cyclic N x N matrix (multi-GPU path): nb x nb blocks over a P x Q grid, this rank (p, q) holds
+// local block (il, jl) = global block (il P + p, jl Q + q) in one ML x NL column-major matrix
+struct CycMap {
+  int on, nb, P, Q, p, q;
+  int64_t ML, NL;
+};
+int launch_kbuild_cyc(const KSpec& ks, const double* X, int64_t ldx, int64_t n, double* T, int64_t ldt, const CycMap& cm,
+                      double jitter, cudaStream_t s, int64_t* launches);
+int launch_symv_cyc(const double* T, int64_t ldt, const CycMap& cm, const double* x, int64_t ldx, int d, double* y,
+                    int64_t ldy, cudaStream_t s, int64_t* launches);
 // K (np x np, ld ldk): lower-triangle tiles of the kernel matrix of X (n valid rows, padded part = identity)
 int launch_kbuild(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, double* K, int64_t ldk,
                   cudaStream_t s, int64_t* launches);
@@ -180,8 +204,10 @@ int launch_kdiag(const KSpec& ks, const double* X, int64_t ldx, int64_t n, doubl
 // gX (n x D, ld ldgx) accumulated with atomics when non-null (must be zeroed by the caller).
 int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, const double* Cg, int64_t ldc,
                 const double* alpha, int64_t lda, int dout, int mode, double* partial, int max_ctas, double* g,
-                double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches, int64_t col0 = -1, int64_t ncols = 0);
+                double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches, int64_t col0 = -1, int64_t ncols = 0,
+                const CycMap* cyc = nullptr);
                 // col0 >= 0: only the lower-triangle tiles of columns [col0, col0+ncols) (multi-GPU column ownership)
+                // cyc: Cg is the LOCAL part of a block-cyclic matrix (ld ldc); X, alpha are the full (replicated) inputs
 // out[i] -= / = helpers for the posterior
 int launch_row_sqnorm_sub(const double* V, int64_t ldv, int64_t rows, int64_t cols, const double* kdiag, double* var,
                           cudaStream_t s, int64_t* launches);  // var[i] = kdiag[i] - sum_j V[i,j]^2

@@ -4,6 +4,7 @@
 //   (CKern.cpp:219-226) and CKern::getGradParams + CGp::updateCovGradient (CGp.cpp:666-679, CKern.cpp:284-298).
 // Squared distances use direct differences (exactly symmetric in (i,j), never negative), the documented
 // deviation from CMatrix::dist2Row's |x|^2+|y|^2-2x.y (CMatrix.h:554-560) -- SURVEY 7 "hard parts".
+#include <string.h>
 #include "common.cuh"
 
 namespace gpc {
@@ -339,6 +340,121 @@ int launch_kcross(const KSpec& ks, const double* X1, int64_t ldx1, int64_t n1, i
   return GPC_OK;
 }
 
+
+// ---- block-cyclic local part of the training kernel matrix (multi-GPU one-sweep path, dist.cu): the N x N matrix is
+// cut into nb x nb blocks dealt to a P x Q process grid; this rank (p, q) stores its blocks as one ML x NL column-major
+// matrix (local block (il, jl) = global block (il P + p, jl Q + q)).  Only blocks on or below the diagonal are written
+// (CGp::_updateK semantics, CGp.cpp:693-712: computeElement off the diagonal, diagComputeElement -- with the white
+// variances -- on it; identity in the padding); diagonal blocks are written in full (both triangles).
+__device__ __forceinline__ void cyc_global(const CycMap& cm, int64_t lr0, int64_t lc0, int64_t& i0, int64_t& j0, int& gi,
+                                           int& gj) {
+  const int64_t il = lr0 / cm.nb, jl = lc0 / cm.nb;
+  gi = (int)(il * cm.P + cm.p);
+  gj = (int)(jl * cm.Q + cm.q);
+  i0 = (int64_t)gi * cm.nb + (lr0 - il * cm.nb);
+  j0 = (int64_t)gj * cm.nb + (lc0 - jl * cm.nb);
+}
+
+__global__ void __launch_bounds__(KTHREADS) kbuild_cyc_kernel(const __grid_constant__ KSpec ks, const double* __restrict__ X,
+                                                             int64_t ldx, int64_t n, double* __restrict__ T, int64_t ldt,
+                                                             const CycMap cm, double jitter) {
+  extern __shared__ double sm[];
+  double* si = sm;
+  double* sj = sm + KT * ks.D;
+  const int64_t lr0 = (int64_t)blockIdx.x * KT, lc0 = (int64_t)blockIdx.y * KT;
+  int64_t i0, j0;
+  int gi, gj;
+  cyc_global(cm, lr0, lc0, i0, j0, gi, gj);
+  if (gi < gj) return;
+  stage_rows(si, X, ldx, n, i0, ks.D);
+  stage_rows(sj, X, ldx, n, j0, ks.D);
+  __syncthreads();
+  const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+  double kv[4][4];
+  eval_pairs(ks, si, sj, ti, tj, kv);
+  const double white = white_sum(ks) + jitter;
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int r = ti + 16 * a, c = tj + 16 * b;
+      const int64_t i = i0 + r, j = j0 + c;
+      double v = kv[a][b];
+      if (i == j) v += white;
+      if (i >= n || j >= n) v = (i == j) ? 1.0 : 0.0;
+      T[(lr0 + r) + (lc0 + c) * ldt] = v;
+    }
+}
+int launch_kbuild_cyc(const KSpec& ks, const double* X, int64_t ldx, int64_t n, double* T, int64_t ldt, const CycMap& cm,
+                      double jitter, cudaStream_t s, int64_t* launches) {
+  static bool configured_dev[64] = {false};
+  size_t smem = (size_t)2 * KT * ks.D * sizeof(double);
+  if (smem > 200 * 1024) {
+    set_error("kbuild_cyc: input dimension too large for the shared-memory stage");
+    return GPC_ERR_ARG;
+  }
+  if (!configured_dev[cur_device() & 63]) {
+    GPC_CUDA_CHECK(cudaFuncSetAttribute(kbuild_cyc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured_dev[cur_device() & 63] = true;
+  }
+  if (cm.ML <= 0 || cm.NL <= 0) return GPC_OK;
+  dim3 grid((unsigned)(cm.ML / KT), (unsigned)(cm.NL / KT));
+  kbuild_cyc_kernel<<<grid, KTHREADS, smem, s>>>(ks, X, ldx, n, T, ldt, cm, jitter);
+  if (launches) (*launches)++;
+  GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("kbuild_cyc_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
+  return GPC_OK;
+}
+
+// y (np x d, ld ldy, zeroed by the caller) += (local part of a symmetric matrix) x.  The local matrix holds the blocks on
+// or below the diagonal (diagonal blocks in full): a strictly-lower block contributes T x_cols to the rows AND T' x_rows
+// to the columns.  One CTA per 64 x 64 tile, tile staged in shared memory, one atomicAdd per (row, output).
+__global__ void __launch_bounds__(256) symv_cyc_kernel(const double* __restrict__ T, int64_t ldt, const CycMap cm,
+                                                      const double* __restrict__ x, int64_t ldx, int d,
+                                                      double* __restrict__ y, int64_t ldy) {
+  __shared__ double st[KT][KT + 1];
+  __shared__ double sxr[KT], sxc[KT];
+  const int64_t lr0 = (int64_t)blockIdx.x * KT, lc0 = (int64_t)blockIdx.y * KT;
+  int64_t i0, j0;
+  int gi, gj;
+  cyc_global(cm, lr0, lc0, i0, j0, gi, gj);
+  if (gi < gj) return;
+  const int tid = threadIdx.x;
+  for (int q = tid; q < KT * KT; q += 256) {
+    const int r = q % KT, c = q / KT;
+    st[r][c] = T[(lr0 + r) + (lc0 + c) * ldt];
+  }
+  const bool offdiag = gi > gj;
+  for (int o = 0; o < d; o++) {
+    __syncthreads();
+    if (tid < KT) sxc[tid] = x[j0 + tid + (int64_t)o * ldx];
+    else if (tid < 2 * KT) sxr[tid - KT] = x[i0 + (tid - KT) + (int64_t)o * ldx];
+    __syncthreads();
+    if (tid < KT) {  // row sums
+      double acc = 0.0;
+#pragma unroll 8
+      for (int c = 0; c < KT; c++) acc = fma(st[tid][c], sxc[c], acc);
+      atomicAdd(&y[i0 + tid + (int64_t)o * ldy], acc);
+    } else if (tid < 2 * KT && offdiag) {  // column sums (the mirrored block)
+      const int c = tid - KT;
+      double acc = 0.0;
+#pragma unroll 8
+      for (int r = 0; r < KT; r++) acc = fma(st[r][c], sxr[r], acc);
+      atomicAdd(&y[j0 + c + (int64_t)o * ldy], acc);
+    }
+  }
+}
+int launch_symv_cyc(const double* T, int64_t ldt, const CycMap& cm, const double* x, int64_t ldx, int d, double* y,
+                    int64_t ldy, cudaStream_t s, int64_t* launches) {
+  if (cm.ML <= 0 || cm.NL <= 0) return GPC_OK;
+  dim3 grid((unsigned)(cm.ML / KT), (unsigned)(cm.NL / KT));
+  symv_cyc_kernel<<<grid, 256, 0, s>>>(T, ldt, cm, x, ldx, d, y, ldy);
+  if (launches) (*launches)++;
+  GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("symv_cyc_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
+  return GPC_OK;
+}
+
 // ---- diag: k(x_i, x_i) with diagComputeElement semantics (white included)
 __global__ void kdiag_kernel(const __grid_constant__ KSpec ks, const double* __restrict__ X, int64_t ldx, int64_t n,
                              double* __restrict__ out) {
@@ -399,7 +515,7 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
                                                        int64_t tc1, const double* __restrict__ Cg, int64_t ldc,
                                                        const double* __restrict__ alpha, int64_t lda, int dout,
                                                        int mode, double* __restrict__ partial, double* __restrict__ gX,
-                                                       int64_t ldgx) {
+                                                       int64_t ldgx, const CycMap cm) {
   extern __shared__ double sm[];
   const int D = ks.D, P = ks.nparams;
   double* si = sm;                       // KT*D
@@ -417,7 +533,10 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
   // the owned column blocks for the multi-GPU path
   const bool whole = (tc0 == 0 && tc1 == ntiles_edge);
   int64_t total;
-  if (whole) {
+  const int64_t cyc_tr = cm.on ? cm.ML / KT : 0;
+  if (cm.on) {
+    total = cyc_tr * (cm.NL / KT);  // every 64 x 64 tile of the local matrix; those above the diagonal are skipped
+  } else if (whole) {
     total = ntiles_edge * (ntiles_edge + 1) / 2;
   } else {
     total = 0;
@@ -427,18 +546,29 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
 
   for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
     int bi, bj;
-    if (whole) {
-      tri_tile(t, bi, bj);
+    int64_t i0, j0;
+    const double* Cgt = Cg;  // addressed with GLOBAL (i, j): Cgt[i + j * ldc]
+    if (cm.on) {
+      const int64_t lr0 = (t % cyc_tr) * KT, lc0 = (t / cyc_tr) * KT;
+      int gi, gj;
+      cyc_global(cm, lr0, lc0, i0, j0, gi, gj);
+      if (gi < gj || i0 + KT - 1 < j0) continue;  // block-uniform
+      Cgt = Cg + (lr0 - i0) + (lc0 - j0) * ldc;
     } else {
-      int64_t rem = t, c = tc0;
-      while (rem >= ntiles_edge - c) {
-        rem -= ntiles_edge - c;
-        c++;
+      if (whole) {
+        tri_tile(t, bi, bj);
+      } else {
+        int64_t rem = t, c = tc0;
+        while (rem >= ntiles_edge - c) {
+          rem -= ntiles_edge - c;
+          c++;
+        }
+        bj = (int)c;
+        bi = (int)(c + rem);
       }
-      bj = (int)c;
-      bi = (int)(c + rem);
+      i0 = (int64_t)bi * KT;
+      j0 = (int64_t)bj * KT;
     }
-    const int64_t i0 = (int64_t)bi * KT, j0 = (int64_t)bj * KT;
     __syncthreads();
     stage_rows(si, X, ldx, n, i0, D);
     stage_rows(sj, X, ldx, n, j0, D);
@@ -463,7 +593,7 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
         int64_t i = i0 + ti + 16 * a, j = j0 + tj + 16 * b;
         double v = 0.0;
         if (i < n && j < n && i >= j) {
-          double cg = Cg[i + j * ldc];
+          double cg = Cgt[i + j * ldc];
           if (mode == 0) {
             double aa = 0.0;
             for (int o = 0; o < dout; o++) aa = fma(sai[o * KT + ti + 16 * a], saj[o * KT + tj + 16 * b], aa);
@@ -696,8 +826,12 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 
 int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, const double* Cg, int64_t ldc,
                 const double* alpha, int64_t lda, int dout, int mode, double* partial, int max_ctas, double* g,
-                double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches, int64_t col0, int64_t ncols) {
+                double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches, int64_t col0, int64_t ncols,
+                const CycMap* cyc) {
   static bool configured_dev[64] = {false};
+  CycMap cm;
+  memset(&cm, 0, sizeof(cm));
+  if (cyc) cm = *cyc;
   if (mode != 0) dout = 0;
   size_t smem = (size_t)(4 * KT * ks.D + 2 * KT * (dout > 0 ? dout : 1) + NWARP * ks.nparams) * sizeof(double);
   if (smem > 200 * 1024) {
@@ -721,12 +855,13 @@ int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_
   }
   int64_t total = 0;
   for (int64_t c = tc0; c < tc1; c++) total += nt - c;
+  if (cm.on) total = (cm.ML / KT) * (cm.NL / KT);
   int ctas = (int)(total < max_ctas ? total : max_ctas);
   if (ctas < 1) ctas = 1;
   const bool wx = gX != nullptr, nd = ks.need_dot != 0;
 #define GPC_GRAD_LAUNCH(WX, ND)                                                                                       \
   grad_kernel<WX, ND><<<ctas, KTHREADS, smem, s>>>(ks, X, ldx, n, nt, tc0, tc1, Cg, ldc, alpha, lda, dout > 0 ? dout : 1, \
-                                                   mode, partial, gX, ldgx)
+                                                   mode, partial, gX, ldgx, cm)
   if (wx && nd) GPC_GRAD_LAUNCH(true, true);
   else if (wx) GPC_GRAD_LAUNCH(true, false);
   else if (nd) GPC_GRAD_LAUNCH(false, true);

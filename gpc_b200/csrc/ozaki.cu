@@ -27,6 +27,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <math.h>
+#include <string.h>
 #include <map>
 #include <mutex>
 #include "common.cuh"
@@ -157,10 +158,18 @@ __global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict
 constexpr int OZ_SL_ROWS = 32;            // rows per slicing block
 constexpr int OZ_SL_STRIDE = OZ_BK + 4;   // 132-byte smem row stride: conflict-free byte scatter for both layouts
 
+// Destination of a slicing pass in the block-cyclic one-sweep mode (dist.cu): the operand is a stack of nb-row blocks;
+// block b goes to slot slot0 + b * slot_stride of the slot buffer (S planes of nb x nb int8, then nb row scales; one
+// slot = slot_rows rows of nb bytes).  nb == 0: the plain [slice][row][k] layout.
+struct OzSlotDst {
+  int nb, slot0, slot_stride, slot_rows;
+};
+
 template <int S>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ g, int64_t ld, int kc, int64_t Rpad,
                                                       int64_t Kpad, const int* __restrict__ emax,
-                                                      int8_t* __restrict__ out, double* __restrict__ scale, int tri) {
+                                                      int8_t* __restrict__ out, double* __restrict__ scale, int tri,
+                                                      const OzSlotDst sd) {
   __shared__ __align__(16) int8_t sm[S * OZ_SL_ROWS * OZ_SL_STRIDE];
   __shared__ double s_inv[OZ_SL_ROWS];
   const int tid = threadIdx.x;
@@ -184,7 +193,13 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
       sc = __longlong_as_double((long long)(Ec + 1) << 52);      // 2^(Ec-1022)
     }
     s_inv[tid] = inv;
-    if (scale_writer) scale[r0 + tid] = sc;
+    if (sd.nb) {
+      const int64_t b = r0 / sd.nb, rr = r0 - b * sd.nb;
+      if (blockIdx.y == 0)
+        reinterpret_cast<double*>(out + (((int64_t)sd.slot0 + b * sd.slot_stride) * sd.slot_rows + (int64_t)S * sd.nb) * sd.nb)[rr + tid] = sc;
+    } else if (scale_writer) {
+      scale[r0 + tid] = sc;
+    }
   }
   __syncthreads();
 #pragma unroll 4
@@ -228,7 +243,13 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     const int r = rem >> 3, ch = rem & 7;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(sm + p * (OZ_SL_ROWS * OZ_SL_STRIDE) + r * OZ_SL_STRIDE + ch * 16);
     uint4 v4 = make_uint4(src[0], src[1], src[2], src[3]);
-    *reinterpret_cast<uint4*>(out + ((int64_t)p * Rpad + r0 + r) * Kpad + k0 + ch * 16) = v4;
+    if (sd.nb) {
+      const int64_t b = r0 / sd.nb, rr = r0 - b * sd.nb;
+      const int64_t row = ((int64_t)sd.slot0 + b * sd.slot_stride) * sd.slot_rows + (int64_t)p * sd.nb + rr + r;
+      *reinterpret_cast<uint4*>(out + row * sd.nb + k0 + ch * 16) = v4;
+    } else {
+      *reinterpret_cast<uint4*>(out + ((int64_t)p * Rpad + r0 + r) * Kpad + k0 + ch * 16) = v4;
+    }
   }
 }
 
@@ -249,6 +270,19 @@ struct OzArgs {
   int kb_lo, kb_hi;      // k-block range of this launch (k is chunked so that the int32 levels cannot overflow)
   int RpadA, RpadB;      // padded row counts (slice stride in the tensor maps)
   int* errflag;
+  // ---- block-cyclic one-sweep mode (dist.cu): C is the LOCAL part of a matrix distributed in nb x nb blocks over a
+  // P x Q process grid (local block (il, jl) = global block (il P + p, jl Q + q)); both operands are block rows of ONE
+  // pre-sliced panel held in "slots" (slot g = global block g: S planes of nb x nb int8, then nb row scales).  Per tile:
+  //   skipped unless global block row >= global block column (and != skip_i / skip_j);
+  //   C = beta' C + alpha' A B',  alpha' = -1 below the panel's step row (i > kstep), +1 at / above it,
+  //                               beta' = 0 in block row kstep and block column kstep, 1 elsewhere.
+  int cyc;               // 0: off
+  int nb, P, Q, p, q;    // block size (multiple of 128) and grid position
+  int kstep;             // global block index of the current panel
+  int skip_i, skip_j;    // global block row / column left out (-1: none): done by a separate (look-ahead) launch
+  int bm0, bn0;          // tile offsets of the launched sub-rectangle inside the local matrix
+  int slot_rows;         // rows (of nb bytes) per slot = S * nb + 8
+  const uint8_t* slots;  // base of the slot buffer (for the row scales)
 };
 
 __device__ __forceinline__ uint32_t oz_elect_one() {
@@ -319,8 +353,34 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     bn = rem / gsz;
   }
   if (a.lower && bn > 2 * bm + 1) return;  // whole CTA, before any barrier / TMEM allocation
+  // operand row coordinates of slice 0 in the tensor maps, slice-to-slice stride, scales, and the per-tile alpha / beta
+  int a_row0, b_row0, a_ss = a.RpadA, b_ss = a.RpadB;
+  const double* scaleA = a.scaleA;
+  const double* scaleB = a.scaleB;
+  double alpha_t = a.alpha, beta_t = a.beta;
+  if (a.cyc) {
+    bm += a.bm0;
+    bn += a.bn0;
+    const int il = (bm * OZ_BM) / a.nb, jl = (bn * OZ_BN) / a.nb;
+    const int gi = il * a.P + a.p, gj = jl * a.Q + a.q;
+    if (gi < gj || gi == a.skip_i || gj == a.skip_j) return;
+    const int ri = bm * OZ_BM - il * a.nb, rj = bn * OZ_BN - jl * a.nb;
+    a_row0 = gi * a.slot_rows + ri;
+    b_row0 = gj * a.slot_rows + rj;
+    a_ss = b_ss = a.nb;
+    scaleA = reinterpret_cast<const double*>(a.slots + ((int64_t)gi * a.slot_rows + (int64_t)a.S * a.nb) * a.nb) + ri;
+    scaleB = reinterpret_cast<const double*>(a.slots + ((int64_t)gj * a.slot_rows + (int64_t)a.S * a.nb) * a.nb) + rj;
+    alpha_t = (gi > a.kstep) ? -1.0 : 1.0;
+    beta_t = (gi == a.kstep || gj == a.kstep) ? 0.0 : 1.0;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = bm * OZ_BM, n0 = bn * OZ_BN;
+  if (!a.cyc) {
+    a_row0 = m0;
+    b_row0 = n0;
+    scaleA += m0;
+    scaleB += n0;
+  }
   int kb0 = a.kb_lo, KB = a.kb_hi;
   if (a.a_tri > 0 && m0 / OZ_BK > kb0) kb0 = m0 / OZ_BK;
   if (a.b_tri > 0 && n0 / OZ_BK > kb0) kb0 = n0 / OZ_BK;
@@ -328,12 +388,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   if (a.b_tri < 0 && (n0 + OZ_BN + OZ_BK - 1) / OZ_BK < KB) KB = (n0 + OZ_BN + OZ_BK - 1) / OZ_BK;
   if (kb0 >= KB) {
     // nothing to accumulate for this tile in this launch: C = beta * C
-    if (a.beta == 1.0) return;
+    if (beta_t == 1.0) return;
     if (tid < OZ_BM) {
       double* crow = a.C + (int64_t)(m0 + tid) + (int64_t)n0 * a.ldc;
       for (int j = 0; j < OZ_BN; j++) {
         double* p = crow + (int64_t)j * a.ldc;
-        *p = (a.beta == 0.0) ? 0.0 : a.beta * (*p);
+        *p = (beta_t == 0.0) ? 0.0 : beta_t * (*p);
       }
     }
     return;
@@ -391,12 +451,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         oz_mbar_expect_tx(FULL_B(set), (uint32_t)S * OZ_B_BYTES);
 #pragma unroll
         for (int q = 0; q < S; q++)
-          oz_tma_load_2d(sB + (uint32_t)(set * S + q) * OZ_B_BYTES, &tmB, FULL_B(set), kb * OZ_BK, q * a.RpadB + n0);
+          oz_tma_load_2d(sB + (uint32_t)(set * S + q) * OZ_B_BYTES, &tmB, FULL_B(set), kb * OZ_BK, q * b_ss + b_row0);
 #pragma unroll
         for (int p = 0; p < S; p++) {
           if (round >= 1) oz_mbar_wait(EMPTY_A(slot), (round - 1) & 1, a.errflag, 2);
           oz_mbar_expect_tx(FULL_A(slot), OZ_A_BYTES);
-          oz_tma_load_2d(sA + slot * OZ_A_BYTES, &tmA, FULL_A(slot), kb * OZ_BK, p * a.RpadA + m0);
+          oz_tma_load_2d(sA + slot * OZ_A_BYTES, &tmA, FULL_A(slot), kb * OZ_BK, p * a_ss + a_row0);
           if (++slot == NA) {
             slot = 0;
             round++;
@@ -437,11 +497,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     __syncwarp();
   } else {
     // ===== epilogue warps 0..3: TMEM lane = output row =====
-    if (tid < OZ_BN) s_cscale[tid] = a.scaleB[n0 + tid];
+    if (tid < OZ_BN) s_cscale[tid] = scaleB[tid];
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int row = warp * 32 + lane;
-    const double rs = a.scaleA[m0 + row] * (1.0 / 4096.0);  // 2^-12: weight of level c = 2
-    const double alpha = a.alpha, beta = a.beta;
+    const double rs = scaleA[row] * (1.0 / 4096.0);  // 2^-12: weight of level c = 2
+    const double alpha = alpha_t, beta = beta_t;
     // the whole C row segment of this thread (64 doubles) is fetched while the tile is still being accumulated: a
     // load issued per chunk after the wait costs a DRAM round trip per chunk on every tile
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
@@ -644,9 +704,9 @@ static int ensure_ws(OzWorkspace& w, int which, size_t bytes, size_t rows) {
 
 template <int S>
 static void launch_slice_t(const double* g, int64_t ld, int kc, int64_t R, int64_t K, const int* emax, int8_t* out,
-                           double* scale, cudaStream_t s, int tri) {
+                           double* scale, cudaStream_t s, int tri, OzSlotDst sd = OzSlotDst{0, 0, 0, 0}) {
   dim3 grid((unsigned)(R / OZ_SL_ROWS), (unsigned)(K / OZ_BK));
-  oz_slice_kernel<S><<<grid, 256, 0, s>>>(g, ld, kc, R, K, emax, out, scale, tri);
+  oz_slice_kernel<S><<<grid, 256, 0, s>>>(g, ld, kc, R, K, emax, out, scale, tri, sd);
 }
 
 static int slice_operand(OzWorkspace& w, int which, const double* g, int64_t ld, bool kc, int64_t R, int64_t K, int S,
@@ -711,6 +771,7 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   GPC_CHECK(make_tmap(&tmA, w.sl[0], (int64_t)S * c.m, c.k, OZ_BM));
   GPC_CHECK(make_tmap(&tmB, w.sl[wb], (int64_t)S * c.n, c.k, OZ_BN));
   OzArgs a;
+  memset(&a, 0, sizeof(a));
   a.C = c.C;
   a.ldc = c.ldc;
   a.scaleA = w.scale[0];
@@ -760,6 +821,124 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   GPC_CUDA_CHECK(cudaEventRecord(w.done, s));
   w.used = true;
   if (trace_sync("oz_gemm_kernel", s) != GPC_OK) return GPC_ERR_CUDA;
+  return GPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Block-cyclic one-sweep mode (dist.cu).  The panel of a step lives in a slot buffer: slot g (global block g) =
+// S planes of nb x nb int8 (k contiguous) followed by nb row scales = slot_rows = S nb + 8 rows of nb bytes.
+// ------------------------------------------------------------------------------------------------------
+size_t oz_slot_bytes(int nb, int S) { return (size_t)(S * nb + 8) * (size_t)nb; }
+
+// slices the stacked operand g (R = nblocks * nb rows, nb deep; kc as in slice_operand) into slots slot0 + b * stride
+int oz_slice_to_slots(const double* g, int64_t ld, bool kc, int64_t R, int nb, int S, int* emax_scratch, uint8_t* slots,
+                      int slot0, int slot_stride, cudaStream_t s, int64_t* launches) {
+  if (R <= 0) return GPC_OK;
+  if (R % nb || nb % OZ_BK || S < 2 || S > OZ_MAXS) {
+    set_error("oz_slice_to_slots: bad shape");
+    return GPC_ERR_ARG;
+  }
+  GPC_CUDA_CHECK(cudaMemsetAsync(emax_scratch, 0, R * sizeof(int), s));
+  int64_t kchunks = (600 + R / 128 - 1) / (R / 128);
+  if (kchunks > nb / 64) kchunks = nb / 64;
+  if (kchunks < 1) kchunks = 1;
+  const int64_t kchunk = (nb + kchunks - 1) / kchunks;
+  dim3 g1((unsigned)(R / 128), (unsigned)kchunks);
+  oz_rowmax_kernel<<<g1, 256, 0, s>>>(g, ld, kc ? 1 : 0, nb, kchunk, emax_scratch, 0);
+  GPC_CUDA_CHECK(cudaGetLastError());
+  OzSlotDst sd{nb, slot0, slot_stride, S * nb + 8};
+  int8_t* out = reinterpret_cast<int8_t*>(slots);
+  switch (S) {
+    case 2: launch_slice_t<2>(g, ld, kc, R, nb, emax_scratch, out, nullptr, s, 0, sd); break;
+    case 3: launch_slice_t<3>(g, ld, kc, R, nb, emax_scratch, out, nullptr, s, 0, sd); break;
+    case 4: launch_slice_t<4>(g, ld, kc, R, nb, emax_scratch, out, nullptr, s, 0, sd); break;
+    case 5: launch_slice_t<5>(g, ld, kc, R, nb, emax_scratch, out, nullptr, s, 0, sd); break;
+    case 6: launch_slice_t<6>(g, ld, kc, R, nb, emax_scratch, out, nullptr, s, 0, sd); break;
+    case 7: launch_slice_t<7>(g, ld, kc, R, nb, emax_scratch, out, nullptr, s, 0, sd); break;
+    default: launch_slice_t<8>(g, ld, kc, R, nb, emax_scratch, out, nullptr, s, 0, sd); break;
+  }
+  GPC_CUDA_CHECK(cudaGetLastError());
+  if (launches) (*launches) += 2;
+  if (trace_sync("oz_slice_kernel(slots)", s) != GPC_OK) return GPC_ERR_CUDA;
+  return GPC_OK;
+}
+
+int oz_cyc_maps(OzCycMaps* out, const uint8_t* slots, int nslots, int nb, int S) {
+  CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(out->opaque);
+  static_assert(sizeof(out->opaque) >= 2 * sizeof(CUtensorMap) + 64, "OzCycMaps too small");
+  // 64-byte aligned placement inside the opaque storage
+  uintptr_t a = (reinterpret_cast<uintptr_t>(out->opaque) + 63) & ~(uintptr_t)63;
+  tm = reinterpret_cast<CUtensorMap*>(a);
+  const int64_t rows = (int64_t)nslots * (S * nb + 8);
+  GPC_CHECK(make_tmap(&tm[0], reinterpret_cast<const int8_t*>(slots), rows, nb, OZ_BM));
+  GPC_CHECK(make_tmap(&tm[1], reinterpret_cast<const int8_t*>(slots), rows, nb, OZ_BN));
+  out->slots = slots;
+  out->nb = nb;
+  out->S = S;
+  return GPC_OK;
+}
+
+// C (local part, ld ldc) updated with the panel in `maps` over the tile sub-rectangle rows [r0, r0 + m), columns
+// [c0, c0 + n) of the local matrix (multiples of 128 / 64); see OzArgs for the per-tile rule.
+int launch_oz_cyc_update(const OzCycMaps& maps, const OzCycGrid& gr, int kstep, int skip_i, int skip_j, double* C,
+                         int64_t ldc, int64_t r0, int64_t m, int64_t c0, int64_t n, int* errflag, cudaStream_t s,
+                         int64_t* launches) {
+  if (m <= 0 || n <= 0) return GPC_OK;
+  const int S = maps.S, nb = maps.nb;
+  if (r0 % OZ_BM || m % OZ_BM || c0 % OZ_BN || n % OZ_BN || nb % OZ_BK || (int64_t)nb / OZ_BK > 128) {
+    set_error("launch_oz_cyc_update: bad tile range / block size");
+    return GPC_ERR_ARG;
+  }
+  uintptr_t al = (reinterpret_cast<uintptr_t>(maps.opaque) + 63) & ~(uintptr_t)63;
+  const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(al);
+  OzArgs a;
+  memset(&a, 0, sizeof(a));
+  a.C = C;
+  a.ldc = ldc;
+  a.alpha = -1.0;
+  a.beta = 1.0;
+  a.tiles_m = (int)(m / OZ_BM);
+  a.tiles_n = (int)(n / OZ_BN);
+  a.kblocks = nb / OZ_BK;
+  a.S = S;
+  a.NA = oz_na(S);
+  a.kb_lo = 0;
+  a.kb_hi = a.kblocks;
+  a.errflag = errflag;
+  a.cyc = 1;
+  a.nb = nb;
+  a.P = gr.P;
+  a.Q = gr.Q;
+  a.p = gr.p;
+  a.q = gr.q;
+  a.kstep = kstep;
+  a.skip_i = skip_i;
+  a.skip_j = skip_j;
+  a.bm0 = (int)(r0 / OZ_BM);
+  a.bn0 = (int)(c0 / OZ_BN);
+  a.slot_rows = S * nb + 8;
+  a.slots = maps.slots;
+  const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
+  switch (S) {
+#define OZ_CASE(SS)                                                                                              \
+  case SS: {                                                                                                     \
+    static bool configured_dev[64] = {false};                                                                    \
+    auto kern = oz_gemm_kernel<SS, oz_na(SS)>;                                                                   \
+    if (!configured_dev[cur_device() & 63]) {                                                                    \
+      GPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem(SS))); \
+      configured_dev[cur_device() & 63] = true;                                                                  \
+    }                                                                                                            \
+    kern<<<(unsigned)ntiles, OZ_THREADS, oz_smem(SS), s>>>(tm[0], tm[1], a);                                     \
+  } break;
+    OZ_CASE(2) OZ_CASE(3) OZ_CASE(4) OZ_CASE(5) OZ_CASE(6) OZ_CASE(7) OZ_CASE(8)
+#undef OZ_CASE
+    default:
+      set_error("launch_oz_cyc_update: slices out of range");
+      return GPC_ERR_ARG;
+  }
+  if (launches) (*launches)++;
+  GPC_CUDA_CHECK(cudaGetLastError());
+  if (trace_sync("oz_gemm_kernel(cyc)", s) != GPC_OK) return GPC_ERR_CUDA;
   return GPC_OK;
 }
 

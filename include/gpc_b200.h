@@ -172,33 +172,46 @@ int gpc_dgemm(int device, char transa, char transb, int64_t m, int64_t n, int64_
 int gpc_dsymv(int device, char uplo, int64_t n, double alpha, const double* A, int64_t lda, const double* x,
               double beta, double* y);
 
-/* ---- device level: the same kernels on CALLER-OWNED device memory and stream.  Used by the multi-GPU path
- *      (gpc_b200/dist.py): PyTorch owns memory, streams and the NCCL collectives; the flops run here.  All dimensions
- *      multiples of 128 (64 for the kernel-matrix column ranges); pointers are DEVICE pointers. ------------------- */
-typedef struct gpc_dev gpc_dev;
-int gpc_dev_create(gpc_dev** out, int device, void* cuda_stream);
-int gpc_dev_destroy(gpc_dev* h);
-int gpc_dev_set_stream(gpc_dev* h, void* cuda_stream);
-int64_t gpc_dev_launch_count(gpc_dev* h);
-/* in-place lower Cholesky of one n x n diagonal block (dpotrf_ on a block of the distributed matrix); Dinv: n x 128
- * inverses of its 128-blocks; base: global row of the block; info_dev / logdet_dev accumulate on the device */
-int gpc_dev_potrf(gpc_dev* h, double* A, int64_t lda, int64_t n, int64_t base, int64_t nvalid, double* Dinv,
-                  int* info_dev, double* logdet_dev);
-/* trans 'T': X L' = B, 'N': X L = B (dtrsm_ right/lower), B in place */
-int gpc_dev_trsm(gpc_dev* h, char trans, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n,
-                 const double* Dinv);
-/* C = alpha op(A) op(B) + beta C; a_kc / b_kc: operand stored with k contiguous; lower bit 0: only lower tiles
- * (m == n); lower bit 1: op(A)(i, kk) is zero for kk < i, so the k loop of each row tile starts at its first row */
-int gpc_dev_gemm(gpc_dev* h, int a_kc, int b_kc, int lower, int64_t m, int64_t n, int64_t k, double alpha,
-                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
-/* columns [col0, col0+ncols) of the training kernel matrix (CGp::_updateK semantics) into K + col0*ldk */
-int gpc_dev_kbuild_cols(gpc_dev* h, const gpc_kcomp* comps, int ncomp, const double* X, int64_t ldx, int64_t n,
-                        int64_t np, int D, int64_t col0, int64_t ncols, double* K, int64_t ldk);
-/* gradient partial sums over the lower-triangle part of columns [col0, col0+ncols) of K^-1 (Cg addresses the full
- * matrix); natural-parameter gradients to HOST g_out (synchronises the stream) */
-int gpc_dev_grad_cols(gpc_dev* h, const gpc_kcomp* comps, int ncomp, const double* X, int64_t ldx, int64_t n, int D,
-                      int64_t col0, int64_t ncols, const double* Cg, int64_t ldc, const double* alpha, int64_t lda,
-                      int dout, double* g_out);
+/* ---- multi-GPU: K, its factor and K^-1 sharded over a P x Q process grid ------------------------------
+ * For N beyond one GPU's memory (the reference cannot even index N = 65536: unsigned int nrows*ncols, CMatrix.cpp:654,
+ * CMatrix.h:232).  The N x N matrix is cut into nb x nb blocks dealt 2-D block-cyclically (rank = p*Q + q owns block (i, j)
+ * iff i % P == p and j % Q == q); each rank stores only its blocks on / below the diagonal (N^2 / (P Q) doubles) and
+ * K -> K^-1 happens in place in ONE right-looking sweep that fuses dpotrf_ and dpotri_ (CMatrix.cpp:371-432,
+ * lapack.h:59-73): per step one panel (diagonal-block factor + its inverse, panel products) is broadcast, already split
+ * into the int8 planes the tensor-core engine consumes, and every rank applies the same rank-nb update to all its blocks.
+ * log det, alpha = K^-1 m and the gradient partial sums are all-reduced.  Same quantities as gpc_eval.
+ * Two back-ends:
+ *   gpc_dist_create_nccl : one PROCESS per GPU (mpirun-style launchers).  Rank 0 calls gpc_dist_unique_id and the
+ *                          launcher hands the 128 bytes to every rank (any transport); collectives = ncclBroadcast /
+ *                          ncclAllReduce on the library's own communicator (libnccl.so.2 is loaded at run time).
+ *   gpc_dist_create_local: ONE process driving ndev devices, a worker thread per device, peer copies over NVLink
+ *                          ordered by CUDA events -- SURVEY 8(b)'s gpc_ctx_create(devices, ndev, ...).  A device may be
+ *                          listed more than once (the block-cyclic logic can be exercised on a single GPU).
+ * Every call on a gpc_dist is collective in the NCCL mode (all ranks call it with the same arguments). */
+typedef struct gpc_dist gpc_dist;
+int gpc_dist_unique_id(void* id128);
+int gpc_dist_create_nccl(gpc_dist** out, int device, int rank, int world, const void* id128, int P, int Q, int64_t N, int D,
+                         int dout, int nb);
+int gpc_dist_create_local(gpc_dist** out, const int* devices, int ndev, int P, int Q, int64_t N, int D, int dout, int nb);
+int gpc_dist_destroy(gpc_dist* h);
+/* X (N x D) and m (N x dout), HOST pointers, replicated to every rank (X is at most a few MB: SURVEY 8(e)) */
+int gpc_dist_set_data(gpc_dist* h, const double* X, int64_t ldx, const double* M, int64_t ldm);
+/* one evaluation: out[0] = logdet, out[1] = quad, out[2] = jitter used (jitChol schedule, CMatrix.cpp:767-804: K is
+ * rebuilt with the accumulated jitter and the sweep repeated); gparams as gpc_eval.  Returns 0, >0 = info, <0 error. */
+int gpc_dist_eval(gpc_dist* h, const gpc_kcomp* comps, int ncomp, double* out, double* gparams);
+/* the blocks of K^-1 this process holds, scattered into a host N x N matrix (both triangles); other entries untouched.
+ * Test hook: with the local back-end the whole matrix comes back, with NCCL each process fills in its own blocks. */
+int gpc_dist_download_kinv(gpc_dist* h, double* dst, int64_t ld);
+/* out8: [ranks, steps (= block rows), bytes of this rank's local matrix, bytes of its two panel buffers, bytes broadcast
+ * per step, kernel launches so far, nb, back-end (0 local, 1 nccl)]; ms5: phases of the last evaluation on this rank
+ * [K build, sweep, alpha, gradient, reductions] */
+int gpc_dist_info(gpc_dist* h, int64_t* out8, double* ms5);
+/* host-only (no GPU needed): what `rank` of a P x Q grid does at step k of the sweep for an N x N problem in nb blocks.
+ * out12 = [block rows NBt, local block rows, local block columns, owns part of block column k, owns part of block row k,
+ * owner of block (k,k), first local block row of its column part (-1), its first slot, number of local block columns of
+ * its row part (-1), first local block row / number of block columns of the look-ahead strips, block row+column the bulk
+ * update leaves out (-1: none)]; producers (NBt ints, may be NULL) = the rank that produces each slot of panel k */
+int gpc_dist_plan(int P, int Q, int rank, int64_t N, int nb, int k, int* out12, int* producers);
 
 /* ---- measurement helpers (bench.py) ----------------------------------------------------------------- */
 /* register-resident DMMA loop: measured fp64 tensor-pipe peak of this device in TFLOP/s */

@@ -27,7 +27,7 @@ def demangle(n):
 
 
 print("static evidence from gpc_b200/csrc/*.o (nvcc -gencode arch=compute_100a,code=sm_100a): python tools/sass_evidence.py\n")
-for src in ("ozaki", "dense", "gpkern", "api", "lapack_api", "api_dev"):
+for src in ("ozaki", "dense", "gpkern", "api", "lapack_api", "dist"):
     obj = os.path.join(CSRC, src + ".o")
     if not os.path.exists(obj):
         continue
