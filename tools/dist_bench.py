@@ -23,7 +23,15 @@ ap.add_argument("--nb", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--n", type=int, default=0, help="override N (first N rows of the workload's inputs)")
 ap.add_argument("--single", action="store_true", help="also time the single-GPU path (gpc_eval)")
+ap.add_argument("--backend", default="local", help="local | nccl (under torchrun: one process per GPU)")
 a = ap.parse_args()
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+if a.backend == "nccl":
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.init_process_group("gloo")
 w = bench.WORKLOADS[a.workload]
 X, y, params = bench.make_inputs(a.workload)
 if a.n:
@@ -31,18 +39,25 @@ if a.n:
 kern = G.make_kern(w["types"], w["D"])
 kern.setParams(params)
 devices = [0] * a.virtual if a.virtual else list(range(a.ngpu))
-grid = default_grid(len(devices))
-gp = DistGp(kern, X, y, grid=grid, nb=a.nb, backend="local", devices=devices)
+if a.backend == "nccl":
+    devices = list(range(world))
+    grid = default_grid(world)
+    gp = DistGp(kern, X, y, grid=grid, nb=a.nb, backend="nccl", device=int(os.environ.get("LOCAL_RANK", "0")))
+else:
+    grid = default_grid(len(devices))
+    gp = DistGp(kern, X, y, grid=grid, nb=a.nb, backend="local", devices=devices)
 ts = []
 for r in range(a.reps):
+    if a.backend == "nccl" and world > 1:
+        dist.barrier()
     t0 = time.time()
     g, ll = gp.logLikelihoodGradient()
     ts.append(time.time() - t0)
 N = X.shape[0]
-out = {"workload": a.workload, "N": N, "devices": devices, "grid": grid, "nb": a.nb, "seconds": ts, "ll": ll,
+out = {"backend": a.backend, "workload": a.workload, "N": N, "devices": devices, "grid": grid, "nb": a.nb, "seconds": ts, "ll": ll,
        "g": list(map(float, g[:4])), "tflops_equiv": N ** 3 / min(ts) / 1e12, "info": gp.info()}
 gp.close()
-if a.single:
+if a.single and rank == 0:
     gp1 = G.CGp(kern, X, y)
     t1 = []
     for r in range(a.reps):
@@ -53,4 +68,7 @@ if a.single:
     out["single_seconds"] = t1
     out["ll_rel_vs_single"] = abs(ll - ll1) / max(1.0, abs(ll1))
     out["g_rel_vs_single"] = float(np.max(np.abs(g - g1) / np.maximum(1.0, np.abs(g1))))
-print(json.dumps(out))
+if rank == 0:
+    print(json.dumps(out))
+if a.backend == "nccl" and world > 1:
+    dist.destroy_process_group()
