@@ -1,9 +1,15 @@
 """tests/golden/make_golden_c3.py -- TEST INFRASTRUCTURE.  ONE run of the compiled, unmodified reference (oracle/_ref,
 oracle/build_ref.sh) on BASELINE.json configs[2] "C3" at its real size: N=32768, D=16, cmpnd(rbfard, white), the
 inputs of bench.make_inputs("c3").  BASELINE.md section 3: "run the reference once for parity (ll, 19
-gradients)".  Needs ~45 GB of host memory and 15-40 minutes on 8 cores; writes tests/golden/c3_reference.json.
+gradients)".  Needs ~45 GB of host memory; writes tests/golden/c3_reference.json.
 
-    python tests/golden/make_golden_c3.py [threads]
+    python tests/golden/make_golden_c3.py 1
+
+RUN IT WITH ONE BLAS THREAD.  The multi-threaded dpotrf_ of the OpenBLAS this container has (scipy's wheel, 0.3.31.dev)
+is broken at n = 32768: on 0.5*ones + I (clearly positive definite) it returns info = 16545 with 7-8 threads and info = 0
+with one (checked with scipy.linalg.lapack.dpotrf directly, 24 s vs 167 s).  Through the reference that surfaces as
+"Matrix non positive definite error" out of CMatrix::jitChol (CMatrix.cpp:767-804) after the jitter schedule gives up.
+Single-threaded the evaluation takes 22 minutes (logLikelihood 828 s, logLikelihoodGradient 510 s).
 """
 import json
 import os
