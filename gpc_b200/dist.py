@@ -85,8 +85,13 @@ class DistGp:
             raise ValueError("backend must be 'nccl' or 'local'")
         self.P, self.Q = P, Q
         self.backend = backend
-        check(L.gpc_dist_set_data(self._h, ptr(X), self.N, ptr(self.m), self.N))
+        self._X = X
+        self.set_data()
         self.jitter = 0.0
+
+    def set_data(self):
+        """(re-)upload X and m from the host to every rank"""
+        check(lib().gpc_dist_set_data(self._h, ptr(self._X), self.N, ptr(self.m), self.N))
 
     def close(self):
         if self._h:
