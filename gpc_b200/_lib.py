@@ -69,12 +69,14 @@ SYMBOLS = [
     "gpc_transform_xtoa", "gpc_transform_gradfact", "gpc_ctx_create", "gpc_ctx_destroy", "gpc_ctx_set_stream",
     "gpc_ctx_get_stream", "gpc_ctx_sync", "gpc_ctx_launch_count", "gpc_set_X", "gpc_set_M", "gpc_set_Y",
     "gpc_kern_build", "gpc_kern_cross", "gpc_kern_diag", "gpc_add_diag", "gpc_potrf", "gpc_jitchol",
-    "gpc_solve_alpha", "gpc_inverse", "gpc_alpha_from_inverse", "gpc_grad", "gpc_kern_grad", "gpc_posterior",
+    "gpc_solve_alpha", "gpc_inverse", "gpc_alpha_from_inverse", "gpc_grad", "gpc_kern_grad", "gpc_kern_grad_cross", "gpc_posterior",
     "gpc_eval", "gpc_download", "gpc_last_timings", "gpc_last_enqueue_ms", "gpc_dpotrf", "gpc_dpotri", "gpc_dtrsm", "gpc_dsyrk",
     "gpc_dgemm", "gpc_dsymv", "gpc_bench_dmma_peak", "gpc_bench_syrk", "gpc_ctx_set_profile", "gpc_last_gemm_profile", "gpc_last_gemm_profile_split", "gpc_bench_gemm",
     "gpc_bench_leaf", "gpc_ctx_dims", "gpc_gp_optimise_scg", "gpc_scg_minimise", "gpc_svml_dims", "gpc_svml_read", "gpc_set_gemm_engine", "gpc_gemm_engine_slices", "gpc_gemm_check", "gpc_oz_slice_check",
     "gpc_gp_model_read", "gpc_gp_model_write", "gpc_gp_model_check_roundtrip", "gpc_gplvm_model_read",
     "gpc_gplvm_model_write",
+    "gpc_sparse_create", "gpc_sparse_destroy", "gpc_sparse_set_data", "gpc_sparse_eval", "gpc_sparse_posterior",
+    "gpc_sparse_launch_count",
     "gpc_dist_unique_id", "gpc_dist_create_nccl", "gpc_dist_create_local", "gpc_dist_destroy", "gpc_dist_set_data",
     "gpc_dist_eval", "gpc_dist_download_kinv", "gpc_dist_info", "gpc_dist_plan",
 ]
@@ -117,6 +119,8 @@ def lib():
     L.gpc_alpha_from_inverse.argtypes = [C.c_void_p, c_double_p]
     L.gpc_grad.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, C.c_void_p]
     L.gpc_kern_grad.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, i64, C.c_void_p, C.c_void_p]
+    L.gpc_kern_grad_cross.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, i64, i64, C.c_void_p, i64, C.c_void_p,
+                                      C.c_void_p]
     L.gpc_posterior.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, i64, i64, C.c_void_p, C.c_void_p]
     L.gpc_eval.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gpc_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, i64]
@@ -155,6 +159,14 @@ def lib():
     L.gpc_oz_slice_check.argtypes = [C.c_int, i64, i64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gpc_gemm_check.argtypes = [C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gpc_sparse_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, i64, C.c_int, C.c_int, C.c_int]
+    L.gpc_sparse_destroy.argtypes = [C.c_void_p]
+    L.gpc_sparse_set_data.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64]
+    L.gpc_sparse_eval.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, i64, C.c_double, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, c_double_p]
+    L.gpc_sparse_posterior.argtypes = [C.c_void_p, C.POINTER(KComp), C.c_int, C.c_void_p, i64, i64, C.c_void_p, C.c_void_p]
+    L.gpc_sparse_launch_count.restype = i64
+    L.gpc_sparse_launch_count.argtypes = [C.c_void_p]
     L.gpc_dist_unique_id.argtypes = [C.c_void_p]
     L.gpc_dist_create_nccl.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, i64,
                                        C.c_int, C.c_int, C.c_int]

@@ -863,6 +863,37 @@ int gpc_kern_grad(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* c
   return GPC_OK;
 }
 
+static int ensure_cross(gpc_ctx* c, int64_t Nsp);
+
+// sum_ij covGrad2[i,j] dk(X_i, X2_j)/dtheta (natural parameters) and, optionally, gX[i,:] = sum_j covGrad2[i,j] dk(X_i,X2_j)/dX_i:
+// CKern::getGradParams(g, X, X2, covGrad) (CKern.h:199-213; rbf CKern.cpp:1204-1241 ...) and the covGrad-weighted
+// CKern::getGradX (CKern.h:68-74), computeElement semantics (white contributes nothing).
+int gpc_kern_grad_cross(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* X2, int64_t N2, int64_t ldx2,
+                        const double* covGrad2, int64_t ldc, double* gparams, double* gX) {
+  GPC_CHECK(need(c, c && c->haveX, "gpc_kern_grad_cross needs X"));
+  if (!X2 || !covGrad2 || !gparams || N2 < 1 || ldx2 < N2 || ldc < c->N) {
+    set_error("gpc_kern_grad_cross: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  KSpec ks;
+  GPC_CHECK(make_kspec(comps, ncomp, c->D, &ks));
+  const int64_t N2p = round_up(N2, TILE);
+  GPC_CHECK(ensure_cross(c, N2p));
+  GPC_CUDA_CHECK(cudaMemsetAsync(c->Xs, 0, (size_t)N2p * c->D * sizeof(double), c->stream));
+  GPC_CHECK(upload(c, c->Xs, N2p, X2, ldx2, N2, c->D));
+  GPC_CHECK(upload(c, c->Kc, c->Np, covGrad2, ldc, c->N, N2));
+  if (gX) GPC_CUDA_CHECK(cudaMemsetAsync(c->gXdev, 0, (size_t)c->Np * c->D * sizeof(double), c->stream));
+  GradCross cx{1, c->Xs, N2p, N2};
+  GPC_CHECK(launch_grad(ks, c->X, c->Np, c->N, c->Np, c->Kc, c->Np, nullptr, 0, 0, 1, c->partial, c->max_ctas,
+                        c->scal + SC_G, gX ? c->gXdev : nullptr, c->Np, c->stream, &c->launches, -1, 0, nullptr, &cx));
+  GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres + SC_G, c->scal + SC_G, ks.nparams * sizeof(double), cudaMemcpyDeviceToHost,
+                                 c->stream));
+  if (gX) GPC_CHECK(download(c, gX, c->N, c->gXdev, c->Np, c->N, c->D));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < ks.nparams; i++) gparams[i] = c->hres[SC_G + i];
+  return GPC_OK;
+}
+
 // V = B L^-T (the right-sided solve V L' = B) through W = L^-1, out of place: one triangular product when W is
 // complete; while the top-level W21 is still deferred the top level is done by block substitution instead
 // (V1 = B1 W11', B2 -= V1 L21', V2 = B2 W22'), which needs only the diagonal halves of W.  B is overwritten.

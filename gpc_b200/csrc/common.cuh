@@ -185,6 +185,13 @@ struct CycMap {
   int on, nb, P, Q, p, q;
   int64_t ML, NL;
 };
+// cross-covariance mode of the gradient pass: sum_ij Cg[i,j] dk(X_i, X2_j)/dtheta and, into gX, d/dX_i
+// (CKern::getGradParams(g, X, X2, covGrad) CKern.h:199-213 and overrides; getGradX CKern.h:68-74)
+struct GradCross {
+  int on;
+  const double* X2;
+  int64_t ldx2, n2;
+};
 int launch_kbuild_cyc(const KSpec& ks, const double* X, int64_t ldx, int64_t n, double* T, int64_t ldt, const CycMap& cm,
                       double jitter, cudaStream_t s, int64_t* launches);
 int launch_symv_cyc(const double* T, int64_t ldt, const CycMap& cm, const double* x, int64_t ldx, int d, double* y,
@@ -205,7 +212,7 @@ int launch_kdiag(const KSpec& ks, const double* X, int64_t ldx, int64_t n, doubl
 int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, const double* Cg, int64_t ldc,
                 const double* alpha, int64_t lda, int dout, int mode, double* partial, int max_ctas, double* g,
                 double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches, int64_t col0 = -1, int64_t ncols = 0,
-                const CycMap* cyc = nullptr);
+                const CycMap* cyc = nullptr, const GradCross* cross = nullptr);
                 // col0 >= 0: only the lower-triangle tiles of columns [col0, col0+ncols) (multi-GPU column ownership)
                 // cyc: Cg is the LOCAL part of a block-cyclic matrix (ld ldc); X, alpha are the full (replicated) inputs
 // out[i] -= / = helpers for the posterior

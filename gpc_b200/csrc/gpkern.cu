@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
                                                        int64_t tc1, const double* __restrict__ Cg, int64_t ldc,
                                                        const double* __restrict__ alpha, int64_t lda, int dout,
                                                        int mode, double* __restrict__ partial, double* __restrict__ gX,
-                                                       int64_t ldgx, const CycMap cm) {
+                                                       int64_t ldgx, const CycMap cm, const GradCross cx) {
   extern __shared__ double sm[];
   const int D = ks.D, P = ks.nparams;
   double* si = sm;                       // KT*D
@@ -534,7 +534,13 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
   const bool whole = (tc0 == 0 && tc1 == ntiles_edge);
   int64_t total;
   const int64_t cyc_tr = cm.on ? cm.ML / KT : 0;
-  if (cm.on) {
+  // cross mode: rows index X (n points), columns index X2 (cx.n2 points), weights Cg are n x n2: every pair counts once,
+  // there is no diagonal (computeElement semantics: white contributes nothing), dL/dX goes to the row inputs only
+  const bool cross = cx.on != 0;
+  const int64_t cross_tr = (n + KT - 1) / KT;
+  if (cross) {
+    total = cross_tr * ((cx.n2 + KT - 1) / KT);
+  } else if (cm.on) {
     total = cyc_tr * (cm.NL / KT);  // every 64 x 64 tile of the local matrix; those above the diagonal are skipped
   } else if (whole) {
     total = ntiles_edge * (ntiles_edge + 1) / 2;
@@ -548,7 +554,10 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
     int bi, bj;
     int64_t i0, j0;
     const double* Cgt = Cg;  // addressed with GLOBAL (i, j): Cgt[i + j * ldc]
-    if (cm.on) {
+    if (cross) {
+      i0 = (t % cross_tr) * KT;
+      j0 = (t / cross_tr) * KT;
+    } else if (cm.on) {
       const int64_t lr0 = (t % cyc_tr) * KT, lc0 = (t / cyc_tr) * KT;
       int gi, gj;
       cyc_global(cm, lr0, lc0, i0, j0, gi, gj);
@@ -571,7 +580,8 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
     }
     __syncthreads();
     stage_rows(si, X, ldx, n, i0, D);
-    stage_rows(sj, X, ldx, n, j0, D);
+    if (cross) stage_rows(sj, cx.X2, cx.ldx2, cx.n2, j0, D);
+    else stage_rows(sj, X, ldx, n, j0, D);
     if (mode == 0) {
       for (int q = tid; q < KT * dout; q += KTHREADS) {
         int o = q / KT, r = q % KT;
@@ -592,7 +602,9 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
       for (int a = 0; a < 4; a++) {
         int64_t i = i0 + ti + 16 * a, j = j0 + tj + 16 * b;
         double v = 0.0;
-        if (i < n && j < n && i >= j) {
+        if (cross) {
+          if (i < n && j < cx.n2) v = Cgt[i + j * ldc];
+        } else if (i < n && j < n && i >= j) {
           double cg = Cgt[i + j * ldc];
           if (mode == 0) {
             double aa = 0.0;
@@ -686,7 +698,7 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
                   double v = sk * ck[a][b] * (xj - xi);
                   if (v != 0.0) {
                     atomicAdd(&sgi[k * KT + ti + 16 * a], v);
-                    atomicAdd(&sgj[k * KT + tj + 16 * b], -v);
+                    if (!cross) atomicAdd(&sgj[k * KT + tj + 16 * b], -v);
                   }
                 }
               }
@@ -783,7 +795,9 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
               // off-diagonal: dL/dx_i gets 2*cg*dk_ij/dx_i = c * dk/dx_i ; dL/dx_j gets c * dk/dx_j
               // diagonal: cg * d k(x_i,x_i)/dx_i = cg * (vi + vj) with i == j
 
-              if (i == j) {
+              if (cross) {
+                atomicAdd(&sgi[k * KT + ti + 16 * a], vi);
+              } else if (i == j) {
                 atomicAdd(&sgi[k * KT + ti + 16 * a], vi + vj);
               } else {
                 atomicAdd(&sgi[k * KT + ti + 16 * a], vi);
@@ -797,7 +811,7 @@ __global__ void __launch_bounds__(KTHREADS, 2) grad_kernel(const __grid_constant
       for (int q = tid; q < KT * D; q += KTHREADS) {
         int k = q / KT, r = q % KT;
         if (i0 + r < n && sgi[q] != 0.0) atomicAdd(&gX[i0 + r + (int64_t)k * ldgx], sgi[q]);
-        if (j0 + r < n && sgj[q] != 0.0) atomicAdd(&gX[j0 + r + (int64_t)k * ldgx], sgj[q]);
+        if (!cross && j0 + r < n && sgj[q] != 0.0) atomicAdd(&gX[j0 + r + (int64_t)k * ldgx], sgj[q]);
       }
     }
   }
@@ -827,11 +841,18 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_t np, const double* Cg, int64_t ldc,
                 const double* alpha, int64_t lda, int dout, int mode, double* partial, int max_ctas, double* g,
                 double* gX, int64_t ldgx, cudaStream_t s, int64_t* launches, int64_t col0, int64_t ncols,
-                const CycMap* cyc) {
+                const CycMap* cyc, const GradCross* cross) {
   static bool configured_dev[64] = {false};
   CycMap cm;
   memset(&cm, 0, sizeof(cm));
   if (cyc) cm = *cyc;
+  GradCross cx;
+  memset(&cx, 0, sizeof(cx));
+  if (cross) {
+    cx = *cross;
+    cx.on = 1;
+    mode = 1;  // caller-supplied weights only
+  }
   if (mode != 0) dout = 0;
   size_t smem = (size_t)(4 * KT * ks.D + 2 * KT * (dout > 0 ? dout : 1) + NWARP * ks.nparams) * sizeof(double);
   if (smem > 200 * 1024) {
@@ -856,12 +877,13 @@ int launch_grad(const KSpec& ks, const double* X, int64_t ldx, int64_t n, int64_
   int64_t total = 0;
   for (int64_t c = tc0; c < tc1; c++) total += nt - c;
   if (cm.on) total = (cm.ML / KT) * (cm.NL / KT);
+  if (cx.on) total = nt * ((cx.n2 + KT - 1) / KT);
   int ctas = (int)(total < max_ctas ? total : max_ctas);
   if (ctas < 1) ctas = 1;
   const bool wx = gX != nullptr, nd = ks.need_dot != 0;
 #define GPC_GRAD_LAUNCH(WX, ND)                                                                                       \
   grad_kernel<WX, ND><<<ctas, KTHREADS, smem, s>>>(ks, X, ldx, n, nt, tc0, tc1, Cg, ldc, alpha, lda, dout > 0 ? dout : 1, \
-                                                   mode, partial, gX, ldgx, cm)
+                                                   mode, partial, gX, ldgx, cm, cx)
   if (wx && nd) GPC_GRAD_LAUNCH(true, true);
   else if (wx) GPC_GRAD_LAUNCH(true, false);
   else if (nd) GPC_GRAD_LAUNCH(false, true);

@@ -205,9 +205,28 @@ class CKern:
         finally:
             ctx.close()
 
-    def getGradTransParams(self, X, covGrad):
-        """CKern::getGradTransParams (CKern.cpp:50-63): gradient w.r.t. the transformed parameters."""
+    def getGradTransParams(self, X, covGrad, X2=None):
+        """CKern::getGradTransParams (CKern.cpp:50-63): gradient w.r.t. the transformed parameters; with X2 the
+        cross-covariance form getGradTransParams(g, X, X2, covGrad2) (testKern.cpp:306-325)."""
+        if X2 is not None:
+            return self.getGradParams2(X, X2, covGrad) * self._gradfacts()
         return self.getGradParams(X, covGrad) * self._gradfacts()
+
+    def getGradParams2(self, X, X2, covGrad2, want_gX=False):
+        """CKern::getGradParams(g, X, X2, covGrad) (CKern.h:199-213 + overrides), natural parameters; with want_gX also
+        gX[i, :] = sum_j covGrad2[i, j] d k(X_i, X2_j) / d X_i -- CKern::getGradX (CKern.h:68-74) contracted with covGrad2."""
+        ctx = self._ctx_for(X)
+        try:
+            arr, n, keep = self._kcomps()
+            X2 = fmat(X2)
+            cg = fmat(covGrad2)
+            g = np.zeros(self.getNumParams())
+            gX = np.zeros((ctx.N, ctx.D), order="F") if want_gX else None
+            check(lib().gpc_kern_grad_cross(ctx.handle, arr, n, ptr(X2), X2.shape[0], X2.shape[0], ptr(cg), cg.shape[0], ptr(g),
+                                            ptr(gX) if want_gX else None))
+            return (g, gX) if want_gX else g
+        finally:
+            ctx.close()
 
 
 class CWhiteKern(CKern):

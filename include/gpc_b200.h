@@ -124,6 +124,12 @@ int gpc_grad(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, double* gparams, d
  * CKern::getGradParams(g, X, covGrad) (CKern.h:187-197 and overrides) -- used by the kernel unit tests */
 int gpc_kern_grad(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, const double* covGrad, int64_t ldc,
                   double* gparams, double* gX);
+/* the cross-covariance form: gparams[P] = sum_ij covGrad2[i,j] dk(X_i, X2_j)/dtheta for HOST X2 (N2 x D) and covGrad2
+ * (N x N2) -- CKern::getGradParams(g, X, X2, covGrad) (CKern.h:199-213 and overrides, exercised by testKern.cpp:306-325,
+ * "g4") -- and, if gX != NULL (N x D, ld N), gX[i,:] = sum_j covGrad2[i,j] dk(X_i, X2_j)/dX_i, the covGrad-weighted
+ * CKern::getGradX (CKern.h:68-74; testKern.cpp:327-362, "G2").  computeElement semantics: white contributes nothing. */
+int gpc_kern_grad_cross(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, const double* X2, int64_t N2, int64_t ldx2,
+                        const double* covGrad2, int64_t ldc, double* gparams, double* gX);
 /* posterior at Xs (Ns x D): mu (Ns x d, ld Ns), var (Ns x d, ld Ns) in the space of m (caller applies
  * scale/bias, CGp.cpp:561-573, 622).  Replaces CGp::posteriorMeanVar (CGp.cpp:642-663): K(X,Xs) build,
  * mu = K*' alpha, var = k(x*,x*) - |L^-1 k*|^2 (dtrsm_, CGp.cpp:603-606).  var may be NULL. */
@@ -171,6 +177,30 @@ int gpc_dgemm(int device, char transa, char transb, int64_t m, int64_t n, int64_
 /* dsymv_ (lapack.h:152-160; CMatrix::symv CMatrix.cpp:127-203) */
 int gpc_dsymv(int device, char uplo, int64_t n, double alpha, const double* A, int64_t lda, const double* x,
               double beta, double* y);
+
+/* ---- sparse approximations of CGp: DTC, DTCVAR, FITC with M inducing inputs --------------------------
+ * CGp.cpp:713-735 (K_uu / K_uf / diag K build), :766-861 (updateAD), :939-988 (logLikelihood), :1146-1223, :1244-1413
+ * (gradients), :490-521, :584-599 (posterior).  approx takes the reference's enum values (CGp.h:13-19): 1 DTC, 2 FITC,
+ * 4 DTCVAR.  One evaluation = K_uu, K_uf (and k_ii) build, two M x M factorisations with explicit inverses, the
+ * O(N M^2) products on the GEMM engines, and the gradient passes over K_uu (symmetric) and K_uf (cross); nothing N x N. */
+typedef struct gpc_sparse gpc_sparse;
+int gpc_sparse_create(gpc_sparse** out, int device, int approx, int64_t N, int M, int D, int dout);
+int gpc_sparse_destroy(gpc_sparse* h);
+/* X (N x D) and m = (y - bias) / scale (N x dout, CGp::updateM CGp.cpp:248-260), HOST pointers */
+int gpc_sparse_set_data(gpc_sparse* h, const double* X, int64_t ldx, const double* M, int64_t ldm);
+/* Xu: M x D inducing inputs (host), beta: the noise precision.  out[0] = log-likelihood exactly as CGp::logLikelihood
+ * returns it (with the reference's constants: -d N/2 log 2pi, counted twice for FITC, CGp.cpp:963 + :1012; without priors and
+ * learnt-scale terms), out[1] = log|Sigma|, out[2] = sum_j m_j' Sigma^-1 m_j, out[3] = sum_i (k_ii - q_ii).
+ * gparams[P]: NATURAL kernel-parameter gradients, component order (multiply by gpc_transform_gradfact); gXu (M x D, ld M):
+ * d ll / d X_u; *gbeta: d ll / d beta (the optimiser's log-beta gradient is beta times it, CGp.cpp:1073-1076).
+ * Returns 0, >0 = info of a factorisation that stayed non positive definite through the jitChol schedule, <0 error. */
+int gpc_sparse_eval(gpc_sparse* h, const gpc_kcomp* comps, int ncomp, const double* Xu, int64_t ldxu, double beta,
+                    double* out, double* gparams, double* gXu, double* gbeta);
+/* mu (Ns x dout, ld Ns) and var (Ns; the same for every output) at HOST Xs (Ns x D), in the space of m; needs a
+ * gpc_sparse_eval at the current parameters.  var may be NULL. */
+int gpc_sparse_posterior(gpc_sparse* h, const gpc_kcomp* comps, int ncomp, const double* Xs, int64_t Ns, int64_t ldxs,
+                         double* mu, double* var);
+int64_t gpc_sparse_launch_count(gpc_sparse* h);
 
 /* ---- multi-GPU: K, its factor and K^-1 sharded over a P x Q process grid ------------------------------
  * For N beyond one GPU's memory (the reference cannot even index N = 65536: unsigned int nrows*ncols, CMatrix.cpp:654,

@@ -121,6 +121,20 @@ def test_trsm_all_sixteen_variants():
                         assert rel_err(got, ref) < 1e-8, (m, n, side, ul, tr, dg)
 
 
+def test_trsm_matlab_fixture_all_sixteen(matrix_mat):
+    """testTrsm (testMatrix.cpp:606-836): the reference's own known answers TRSM1..16 of matfiles/trsmMatrixTest.mat, in its
+    order -- (L | L2 | U | U2) x (left | right) x (N | T) x (non-unit | unit) -- at its tolerance 1e-8 absolute."""
+    f = matrix_mat
+    B, alpha = f["trsmMatrixTest_B"], float(np.ravel(f["trsmMatrixTest_alpha"])[0])
+    order = [("L", "l", "l", "n", "n"), ("L", "l", "l", "t", "n"), ("L2", "r", "l", "n", "n"), ("L2", "r", "l", "t", "n"),
+             ("L", "l", "l", "n", "u"), ("L", "l", "l", "t", "u"), ("L2", "r", "l", "n", "u"), ("L2", "r", "l", "t", "u"),
+             ("U", "l", "u", "n", "n"), ("U", "l", "u", "t", "n"), ("U2", "r", "u", "n", "n"), ("U2", "r", "u", "t", "n"),
+             ("U", "l", "u", "n", "u"), ("U", "l", "u", "t", "u"), ("U2", "r", "u", "n", "u"), ("U2", "r", "u", "t", "u")]
+    for k, (mat, side, ul, tr, dg) in enumerate(order, start=1):
+        got = M.trsm(B, f["trsmMatrixTest_" + mat], alpha, side, ul, tr, dg)
+        assert np.abs(got - f["trsmMatrixTest_TRSM%d" % k]).max() < 1e-8, (k, mat, side, ul, tr, dg)
+
+
 def test_potrf_sizes_and_nonpd():
     rng = np.random.default_rng(3)
     for n in [1, 5, 127, 128, 129, 300, 1000, 2050]:
@@ -322,6 +336,34 @@ def test_full_size_properties(N, D, kind):
     gp.setOptParams(tp - h * dvec)
     lm = gp.logLikelihood()
     assert abs((lp - lm) / (2 * h) - float(g @ dvec)) < 1e-4 * max(1.0, abs(float(g @ dvec)))
+
+
+def test_wide_dynamic_range_evaluation_on_the_tensor_core_engine():
+    """The tensor-core fp64 engine is exact relative to each operand ROW's largest entry (ozaki.cu), not element-wise.
+    A kernel matrix whose rows span many decades -- poly + lin with large weights over inputs of very different norms,
+    plus a tiny white term -- is the adversarial case for that; the engine is forced on for every product large enough
+    (gpc_set_gemm_engine) and the full evaluation must still meet the 1e-8 bar against the oracle (N = 1536: the
+    factorisation's GEMMs go through the engine)."""
+    from gpc_b200._lib import lib
+    rng = np.random.default_rng(21)
+    N, D = 1536, 3
+    X = rng.standard_normal((N, D)) * np.exp(rng.uniform(-3.0, 1.5, size=(N, 1)))   # row norms over 4.5 e-folds
+    y = np.tanh(X[:, :1]) + 0.05 * rng.standard_normal((N, 1))
+    types = ["poly", "lin", "rbf", "white"]
+    tp = np.array([np.log(3.0), np.log(1e-4), np.log(5.0), np.log(4.0), 0.0, 0.0, 0.0])
+    kern_o = O.kern_from_trans(types, tp, D)
+    Kd = O.kern_compute(kern_o, X)
+    # entries over 11 decades, a typical row over 5, cond(K) = 6e6 (so that 1e-8 is a fair bar for fp64)
+    assert Kd.max() / np.abs(Kd).min() > 1e10 and np.median(np.abs(Kd).max(1) / np.abs(Kd).min(1)) > 1e5
+    lib().gpc_set_gemm_engine(1, 8, 128, 128)      # tensor-core engine for everything from 128 x 128 x 128 up
+    try:
+        gp = G.CGp(G.make_kern(types, D, tp), X, y, bias=y.mean(0))
+        g, ll = gp.logLikelihoodGradient()
+    finally:
+        lib().gpc_set_gemm_engine(1, 8, 256, 512)  # defaults (ozaki.cu)
+    r = O.gp_loglik_grad(kern_o, X, y, bias=y.mean(0))
+    assert rel_err(ll, r["ll"]) < 1e-8
+    assert rel_err(g, r["g"]) < 1e-8
 
 
 def test_gplvm_scg_trajectory_config5():
