@@ -245,9 +245,10 @@ static Dense sp_dense(gpc_sparse* h, double* W) {
 }
 
 // L L' = S (lower of S read), W = L^-1, *logdet = log|S|; the jitChol schedule on failure (CMatrix.cpp:767-804: S mutated)
-static int sp_factor(gpc_sparse* h, double* S, double* L, double* W, double* logdet) {
+static int sp_factor(gpc_sparse* h, double* S, double* L, double* W, double* logdet, double* jitter_added) {
   const int64_t Mp = h->Mp;
   double jitter = 0.0;
+  *jitter_added = 0.0;
   for (int tries = 0;; tries++) {
     GPC_CUDA_CHECK(cudaMemsetAsync(h->info, 0, sizeof(int), h->s));
     GPC_CUDA_CHECK(cudaMemsetAsync(h->scal + SS_LOGDET, 0, sizeof(double), h->s));
@@ -268,6 +269,7 @@ static int sp_factor(gpc_sparse* h, double* S, double* L, double* W, double* log
       jitter = 1e-6 * tr / (double)h->M;
     }
     GPC_CHECK(launch_add_diag(S, Mp, h->M, jitter, h->s, &h->launches));
+    *jitter_added += jitter;
     jitter *= 10.0;
     if (jitter > 10.0 || tries + 1 >= 20) {
       set_error("sparse GP: matrix is non positive definite after jitter retries");
@@ -424,9 +426,9 @@ int gpc_sparse_eval(gpc_sparse* h, const gpc_kcomp* comps, int ncomp, const doub
   GPC_CUDA_CHECK(cudaMemsetAsync(h->kdiag, 0, (size_t)Np * sizeof(double), s));
   if (fitc || dtcvar) GPC_CHECK(launch_kdiag(ks, h->X, Np, N, h->kdiag, s, &h->launches));
   // ---- 2. K_uu = L_u L_u', W_u; B = K_uu^-1 K_uf; q_ii
-  double logdetKuu = 0.0, logdetA = 0.0;
+  double logdetKuu = 0.0, logdetA = 0.0, jitKuu = 0.0, jitA = 0.0;
   {
-    int rc = sp_factor(h, h->Kuu, h->Lu, h->Wu, &logdetKuu);
+    int rc = sp_factor(h, h->Kuu, h->Lu, h->Wu, &logdetKuu, &jitKuu);
     if (rc != GPC_OK) return rc;
   }
   GPC_CHECK(sp_solve(h, h->Wu, h->Kuf, h->V, h->B));
@@ -446,7 +448,7 @@ int gpc_sparse_eval(gpc_sparse* h, const gpc_kcomp* comps, int ncomp, const doub
     GPC_CHECK(launch_gemm(g, s, &h->launches));
   }
   {
-    int rc = sp_factor(h, h->A, h->LA, h->WA, &logdetA);
+    int rc = sp_factor(h, h->A, h->LA, h->WA, &logdetA, &jitA);
     if (rc != GPC_OK) return rc;
   }
   GPC_CHECK(sp_inverse(h, h->WA, h->Ainv));
@@ -460,10 +462,20 @@ int gpc_sparse_eval(gpc_sparse* h, const gpc_kcomp* comps, int ncomp, const doub
     dim3 g((unsigned)((Mp + 127) / 128), (unsigned)((Np + chunk - 1) / chunk));
     sp_matvec_rows_kernel<<<g, 128, 0, s>>>(h->KufL, Mp, Np, h->Mt, Np, d, h->t1, Mp, chunk);
     SP_LAUNCH_CHECK("sp_matvec_rows_kernel");
+  }
+  // t2 = A^-1 t1 as W_A' (W_A t1), NOT through the explicit A^-1: t1 = K_uf Lambda^-1 m lives in A's large eigen-directions, so
+  // A^-1 t1 is tiny against |A^-1| |t1| and the product with the full inverse would lose cond(A) eps of the quadratic form
+  // (the reference's own dsymv_ with Ainv, CGp.cpp:948-949, does; the triangular products do not)
+  GPC_CHECK(launch_gemv_rows(h->WA, Mp, Mp, Mp, h->t1, Mp, d, h->Ba, Mp, s, &h->launches));  // Ba as scratch: u = W_A t1
+  sp_matvec_cols_kernel<<<(unsigned)((Mp + 7) / 8), 256, 0, s>>>(h->WA, Mp, Mp, h->Ba, Mp, d, h->t2, Mp);
+  SP_LAUNCH_CHECK("sp_matvec_cols_kernel");
+  GPC_CUDA_CHECK(cudaMemsetAsync(h->Ba, 0, (size_t)Mp * d * sizeof(double), s));
+  {
+    const int64_t chunk = 512;
+    dim3 g((unsigned)((Mp + 127) / 128), (unsigned)((Np + chunk - 1) / chunk));
     sp_matvec_rows_kernel<<<g, 128, 0, s>>>(h->BS, Mp, Np, h->Mt, Np, d, h->Ba, Mp, chunk);
     SP_LAUNCH_CHECK("sp_matvec_rows_kernel");
   }
-  GPC_CHECK(launch_symm_small(h->Ainv, Mp, h->t1, Mp, h->t2, Mp, Mp, d, h->symm_part, s, &h->launches));  // t2 = A^-1 t1
   sp_matvec_cols_kernel<<<cgrid, 256, 0, s>>>(h->KufL, Mp, Np, h->t2, Mp, d, h->ta, Np);
   SP_LAUNCH_CHECK("sp_matvec_cols_kernel");
   sp_a_kernel<<<(unsigned)((Np + 255) / 256), 256, 0, s>>>(h->a, h->Mt, h->ta, h->linv, Np, d);
@@ -546,6 +558,8 @@ int gpc_sparse_eval(gpc_sparse* h, const gpc_kcomp* comps, int ncomp, const doub
     out[1] = logdet;
     out[2] = quad;
     out[3] = (double)skq;
+    out[4] = jitKuu;
+    out[5] = jitA;
   }
   if (gparams)
     for (int i = 0; i < ks.nparams; i++)

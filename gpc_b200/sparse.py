@@ -30,7 +30,7 @@ class SparseGp:
         self._h = C.c_void_p()
         check(lib().gpc_sparse_create(C.byref(self._h), device, APPROX[self.approx], self.N, self.M, self.D, self.d))
         check(lib().gpc_sparse_set_data(self._h, ptr(X), self.N, ptr(self.m), self.N))
-        self._out = np.zeros(4)
+        self._out = np.zeros(6)
 
     def close(self):
         if self._h:

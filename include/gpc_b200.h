@@ -190,7 +190,8 @@ int gpc_sparse_destroy(gpc_sparse* h);
 int gpc_sparse_set_data(gpc_sparse* h, const double* X, int64_t ldx, const double* M, int64_t ldm);
 /* Xu: M x D inducing inputs (host), beta: the noise precision.  out[0] = log-likelihood exactly as CGp::logLikelihood
  * returns it (with the reference's constants: -d N/2 log 2pi, counted twice for FITC, CGp.cpp:963 + :1012; without priors and
- * learnt-scale terms), out[1] = log|Sigma|, out[2] = sum_j m_j' Sigma^-1 m_j, out[3] = sum_i (k_ii - q_ii).
+ * learnt-scale terms), out[1] = log|Sigma|, out[2] = sum_j m_j' Sigma^-1 m_j, out[3] = sum_i (k_ii - q_ii),
+ * out[4], out[5] = jitter the jitChol schedule added to K_uu and to A (0 normally; CGp.cpp:777, 830 call jitChol on A).
  * gparams[P]: NATURAL kernel-parameter gradients, component order (multiply by gpc_transform_gradfact); gXu (M x D, ld M):
  * d ll / d X_u; *gbeta: d ll / d beta (the optimiser's log-beta gradient is beta times it, CGp.cpp:1073-1076).
  * Returns 0, >0 = info of a factorisation that stayed non positive definite through the jitChol schedule, <0 error. */

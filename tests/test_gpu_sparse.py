@@ -93,28 +93,23 @@ def test_sparse_random_vs_oracle_across_tile_edges(approx):
     gp.close()
 
 
-def test_sparse_large_n_properties():
-    """N = 100 000, M = 1024 (the regime the approximation exists for): DTC against its own dense definition on a sample is
-    not affordable on the host, so: finite differences of ll along a random direction of [kernel, log beta], and FITC == DTC
-    when k_ii - q_ii vanishes is not available either -- the directional derivative is the size-independent property."""
+@pytest.mark.parametrize("approx", ["dtc", "fitc"])
+def test_sparse_large_n_vs_oracle(approx):
+    """N = 100 000, M = 1024 -- the regime the approximation exists for (every M x M x N product on the tensor-core engine).
+    The oracle still runs there in ~10 s of host time (it is O(N M^2)).  cond(A) is 1e7 at this size, so the inducing-input
+    gradient, the most sensitive output, is held to 1e-6; ll and the kernel / beta gradients to the usual bars."""
     rng = np.random.default_rng(3)
     N, M, D = 100000, 1024, 4
     X = rng.standard_normal((N, D))
     y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((N, 1))
     Xu = X[rng.choice(N, M, replace=False)].copy()
-    gp = SparseGp(G.make_kern(["rbf", "white"], D, [np.log(0.5), 0.0, np.log(1e-3)]), X, y, Xu, 50.0, "fitc", bias=y.mean(0))
+    types, tp, beta = ["rbf", "white"], np.array([np.log(0.5), 0.0, np.log(0.1)]), 10.0
+    gp = SparseGp(G.make_kern(types, D, tp), X, y, Xu, beta, approx, bias=y.mean(0))
     g, ll = gp.logLikelihoodGradient()
-    assert np.isfinite(ll) and np.isfinite(g).all()
-    p0 = gp.getOptParams()
-    dvec = np.zeros_like(p0)
-    dvec[M * D:] = rng.standard_normal(4)
-    dvec /= np.linalg.norm(dvec)
-    h = 1e-5
-    gp.setOptParams(p0 + h * dvec)
-    lp = gp.logLikelihood()
-    gp.setOptParams(p0 - h * dvec)
-    lm = gp.logLikelihood()
-    assert abs((lp - lm) / (2 * h) - float(g @ dvec)) <= 2e-5 * max(1.0, abs(float(g @ dvec)))
+    r = S.sparse_loglik_grad(O.kern_from_trans(types, tp, D), X, y, Xu, beta, approx, bias=y.mean(0))
+    assert abs(ll - r["ll"]) <= 1e-9 * abs(r["ll"])
+    assert rel_err(g[M * D:], r["g"][M * D:]) <= 1e-7
+    assert rel_err(g[:M * D], r["g"][:M * D]) <= 1e-6
     gp.close()
 
 
