@@ -123,7 +123,9 @@ def test_trsm_all_sixteen_variants():
 
 def test_trsm_matlab_fixture_all_sixteen(matrix_mat):
     """testTrsm (testMatrix.cpp:606-836): the reference's own known answers TRSM1..16 of matfiles/trsmMatrixTest.mat, in its
-    order -- (L | L2 | U | U2) x (left | right) x (N | T) x (non-unit | unit) -- at its tolerance 1e-8 absolute."""
+    order -- (L | L2 | U | U2) x (left | right) x (N | T) x (non-unit | unit) -- at its tolerance 1e-8, taken relative to the
+    largest expected entry: the unit-diagonal and U2 cases have solutions of size 1e12 (the fixture's triangular factors are
+    random, not well conditioned), where 1e-8 absolute is below one ulp."""
     f = matrix_mat
     B, alpha = f["trsmMatrixTest_B"], float(np.ravel(f["trsmMatrixTest_alpha"])[0])
     order = [("L", "l", "l", "n", "n"), ("L", "l", "l", "t", "n"), ("L2", "r", "l", "n", "n"), ("L2", "r", "l", "t", "n"),
@@ -132,7 +134,8 @@ def test_trsm_matlab_fixture_all_sixteen(matrix_mat):
              ("U", "l", "u", "n", "u"), ("U", "l", "u", "t", "u"), ("U2", "r", "u", "n", "u"), ("U2", "r", "u", "t", "u")]
     for k, (mat, side, ul, tr, dg) in enumerate(order, start=1):
         got = M.trsm(B, f["trsmMatrixTest_" + mat], alpha, side, ul, tr, dg)
-        assert np.abs(got - f["trsmMatrixTest_TRSM%d" % k]).max() < 1e-8, (k, mat, side, ul, tr, dg)
+        want = f["trsmMatrixTest_TRSM%d" % k]
+        assert np.abs(got - want).max() < 1e-8 * max(1.0, np.abs(want).max()), (k, mat, side, ul, tr, dg)
 
 
 def test_potrf_sizes_and_nonpd():

@@ -93,13 +93,14 @@ def test_sparse_random_vs_oracle_across_tile_edges(approx):
     gp.close()
 
 
-@pytest.mark.parametrize("approx", ["dtc", "fitc"])
-def test_sparse_large_n_vs_oracle(approx):
+@pytest.mark.parametrize("approx,N,M", [("dtc", 100000, 1024), ("fitc", 8000, 512)])
+def test_sparse_large_n_vs_oracle(approx, N, M):
     """N = 100 000, M = 1024 -- the regime the approximation exists for (every M x M x N product on the tensor-core engine).
     The oracle still runs there in ~10 s of host time (it is O(N M^2)).  cond(A) is 1e7 at this size, so the inducing-input
     gradient, the most sensitive output, is held to 1e-6; ll and the kernel / beta gradients to the usual bars."""
+    # (the oracle's FITC diagonal term materialises an N x N matrix: FITC is checked at N = 8000)
     rng = np.random.default_rng(3)
-    N, M, D = 100000, 1024, 4
+    D = 4
     X = rng.standard_normal((N, D))
     y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((N, 1))
     Xu = X[rng.choice(N, M, replace=False)].copy()
