@@ -50,6 +50,8 @@ CGpB200::~CGpB200()
 {
   if(dev)
     gpc_ctx_destroy(dev);
+  if(sdev)
+    gpc_sparse_destroy(sdev);
 }
 void CGpB200::init()
 {
@@ -61,6 +63,13 @@ void CGpB200::init()
   keyX = keyY = 0;
   evalOut[0] = evalOut[1] = evalOut[2] = 0.0;
   nEvals = 0;
+  sdev = 0;
+  sN = 0;
+  sM = sD = sd = sApprox = 0;
+  sstate = STALE;
+  sgBeta = 0.0;
+  for(int i = 0; i < 6; i++)
+    spOut[i] = 0.0;
 }
 void CGpB200::setDevice(int d)
 {
@@ -76,6 +85,7 @@ void CGpB200::setDevice(int d)
 void CGpB200::fail(int rc) const
 {
   state = STALE;
+  sstate = STALE;
   if(rc > 0)
     throw ndlexceptions::MatrixNonPosDef(); // what CMatrix::potrf / jitChol throw (CMatrix.cpp:378, 791, 801)
   throw ndlexceptions::Error(std::string("gpc_b200: ") + gpc_last_error());
@@ -196,8 +206,110 @@ void CGpB200::ensureFactored() const
   state = FACTORED;
 }
 
+// ---- sparse approximations (DTC / FITC / DTCVAR) ---------------------------------------------------------------------
+bool CGpB200::onDeviceSparse() const
+{
+  int a = getApproximationType();
+  if(!isSparseApproximation() || !(a == DTC || a == FITC || a == DTCVAR))
+    return false;
+  if(isOptimiseX() || isBackConstrained() || !isSpherical() || isOutputScaleLearnt())
+    return false;
+  if(!pX || !py || !getKernel() || getNumActive() == 0 || X_u.getRows() != getNumActive())
+    return false;
+  return bridge.sync(getKernel(), pX->getCols());
+}
+
+bool CGpB200::sameSparseInputs() const
+{
+  if(keyX != pX || keyY != py || !sdev)
+    return false;
+  const std::vector<double>& p = bridge.naturalParams();
+  const CMatrix& mm = this->*memberOf(CGpMTag());
+  unsigned int d = getOutputDim();
+  size_t nm = (size_t)mm.getRows() * mm.getCols(), nu = (size_t)X_u.getRows() * X_u.getCols();
+  if(skey.size() != p.size() + 2 * d + 1 + nu + nm)
+    return false;
+  size_t c = 0;
+  for(size_t i = 0; i < p.size(); i++)
+    if(skey[c++] != p[i])
+      return false;
+  for(unsigned int j = 0; j < d; j++)
+    if(skey[c++] != getScaleVal(j))
+      return false;
+  for(unsigned int j = 0; j < d; j++)
+    if(skey[c++] != getBiasVal(j))
+      return false;
+  if(skey[c++] != getBetaVal())
+    return false;
+  const double* uv = X_u.getVals();
+  for(size_t i = 0; i < nu; i++)
+    if(skey[c++] != uv[i])
+      return false;
+  const double* mv = mm.getVals();
+  for(size_t i = 0; i < nm; i++)
+    if(skey[c++] != mv[i])
+      return false;
+  return true;
+}
+
+void CGpB200::ensureSparseEvaluated() const
+{
+  if(sstate == EVALUATED && sameSparseInputs())
+    return;
+  DIMENSIONMATCH(py->getRows() == pX->getRows());
+  int64_t N = pX->getRows();
+  int D = (int)pX->getCols(), d = (int)py->getCols(), M = (int)getNumActive(), a = getApproximationType();
+  const CMatrix& mm = this->*memberOf(CGpMTag());
+  if(!sdev || N != sN || D != sD || d != sd || M != sM || a != sApprox)
+  {
+    if(sdev)
+      gpc_sparse_destroy(sdev);
+    sdev = 0;
+    // the library takes the reference's enum values (CGp.h:13-19): DTC = 1, FITC = 2, DTCVAR = 4
+    int rc = gpc_sparse_create(&sdev, device, a, N, M, D, d);
+    if(rc)
+      fail(rc);
+    sN = N;
+    sD = D;
+    sd = d;
+    sM = M;
+    sApprox = a;
+    keyX = 0;
+  }
+  // X and the reference's own m (see upload() for why m is taken as CGp::updateM left it)
+  int rc = gpc_sparse_set_data(sdev, pX->getVals(), N, mm.getVals(), N);
+  if(rc)
+    fail(rc);
+  sgNat.assign(bridge.getNumParams(), 0.0);
+  sgXu.assign((size_t)M * D, 0.0);
+  rc = gpc_sparse_eval(sdev, bridge.comps(), bridge.numComps(), X_u.getVals(), M, getBetaVal(), spOut, &sgNat[0], &sgXu[0],
+                       &sgBeta);
+  if(rc)
+    fail(rc);
+  if((spOut[4] > 1e-2 || spOut[5] > 1e-2) && getVerbosity() > 2) // CGp.cpp:778-780, 831-833
+    cout << "Warning: jitter of " << (spOut[5] > spOut[4] ? spOut[5] : spOut[4]) << " added to A in updateAD()." << endl;
+  skey = bridge.naturalParams();
+  for(unsigned int j = 0; j < getOutputDim(); j++)
+    skey.push_back(getScaleVal(j));
+  for(unsigned int j = 0; j < getOutputDim(); j++)
+    skey.push_back(getBiasVal(j));
+  skey.push_back(getBetaVal());
+  skey.insert(skey.end(), X_u.getVals(), X_u.getVals() + (size_t)X_u.getRows() * X_u.getCols());
+  skey.insert(skey.end(), mm.getVals(), mm.getVals() + (size_t)mm.getRows() * mm.getCols());
+  keyX = pX;
+  keyY = py;
+  sstate = EVALUATED;
+  nEvals++;
+}
+
 double CGpB200::logLikelihood() const
 {
+  if(onDeviceSparse())
+  {
+    ensureSparseEvaluated();
+    // spOut[0] already is -1/2 (...) - d N/2 log 2pi with the reference's constants (CGp.cpp:939-988, 1009-1012)
+    return spOut[0] + getKernel()->priorLogProb();
+  }
   if(!onDevice())
     return CGp::logLikelihood();
   ensureEvaluated();
@@ -214,6 +326,25 @@ double CGpB200::logLikelihood() const
 
 double CGpB200::logLikelihoodGradient(CMatrix& g) const
 {
+  if(onDeviceSparse())
+  {
+    if(!isMupToDate())
+      throw ndlexceptions::Error("updateG() called when M is not updated.");
+    ensureSparseEvaluated();
+    DIMENSIONMATCH(g.getRows() == 1 && g.getCols() == getOptNumParams());
+    g.zeros();
+    unsigned int counter = 0;
+    if(!isInducingFixed()) // [X_u column-major] (CGp.cpp:1043-1055)
+      for(size_t i = 0; i < sgXu.size(); i++)
+        g.setVal(sgXu[i], 0, counter++);
+    std::vector<double> gk(sgNat);
+    bridge.finishGradient(getKernel(), &gk[0]); // transforms and prior gradients, as CKern::getGradTransParams
+    for(unsigned int i = 0; i < bridge.getNumParams(); i++)
+      g.setVal(gk[i], 0, counter++);
+    // log beta: gBeta * gradfact(beta) with the exp transform beta carries (CGp.cpp:1071-1076, CTransform.cpp:50-53)
+    g.setVal(sgBeta * getBetaVal(), 0, counter++);
+    return logLikelihood();
+  }
   if(!onDevice())
     return CGp::logLikelihoodGradient(g);
   if(!isMupToDate()) // CGp::updateG (CGp.cpp:1082-1083)
@@ -242,10 +373,34 @@ void CGpB200::updateX()
 {
   CGp::updateX();
   state = STALE; // *pX changed in place
+  sstate = STALE;
 }
 
 void CGpB200::posteriorMeanVar(CMatrix& mu, CMatrix& varSigma, const CMatrix& Xin) const
 {
+  if(onDeviceSparse())
+  {
+    DIMENSIONMATCH(mu.getCols() == getOutputDim() && varSigma.getCols() == getOutputDim());
+    DIMENSIONMATCH(mu.getRows() == Xin.getRows() && varSigma.getRows() == Xin.getRows());
+    DIMENSIONMATCH(Xin.getCols() == pX->getCols());
+    ensureSparseEvaluated();
+    std::vector<double> v(Xin.getRows());
+    int rc = gpc_sparse_posterior(sdev, bridge.comps(), bridge.numComps(), Xin.getVals(), Xin.getRows(), Xin.getRows(),
+                                  mu.getVals(), &v[0]);
+    if(rc)
+      fail(rc);
+    for(unsigned int j = 0; j < getOutputDim(); j++)
+    {
+      double scaleVal = getScaleVal(j), biasVal = getBiasVal(j); // CGp.cpp:561-573, 618-626
+      for(unsigned int i = 0; i < varSigma.getRows(); i++)
+        varSigma.setVal(v[i] * scaleVal * scaleVal, i, j);
+      if(scaleVal != 1.0)
+        mu.scaleCol(j, scaleVal);
+      if(biasVal != 0.0)
+        mu.addCol(j, biasVal);
+    }
+    return;
+  }
   if(!onDevice())
   {
     CGp::posteriorMeanVar(mu, varSigma, Xin);
@@ -282,7 +437,7 @@ void CGpB200::posteriorMeanVar(CMatrix& mu, CMatrix& varSigma, const CMatrix& Xi
 
 void CGpB200::posteriorMean(CMatrix& mu, const CMatrix& Xin) const
 {
-  if(!onDevice())
+  if(!onDevice() && !onDeviceSparse())
   {
     CGp::posteriorMean(mu, Xin);
     return;

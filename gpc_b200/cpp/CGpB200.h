@@ -12,8 +12,11 @@
 // out) are redeclared here so that code holding a CGpB200 uses the device too.  CGp::optimise and every optimiser of
 // COptimisable (SCG, CG, GD, BFGS) are inherited as they are: they only see the virtuals.
 //
-// Anything outside the device path -- sparse approximations (DTC/FITC/PITC), kernel components the library does not
-// implement, optimiseX on a CGp -- falls through to the inherited host implementation, call by call.
+// The sparse approximations DTC / FITC / DTCVAR (CGp.cpp:713-861, 939-988, 1146-1413) take the same route through
+// gpc_sparse_eval / gpc_sparse_posterior (K_uu, K_uf, the two M x M factorisations, the O(N M^2) products and the gradient
+// passes on the device; the optimiser's [X_u][kernel][log beta] layout assembled here).
+// Anything outside the device path -- PITC, a learnt output scale on a sparse model, kernel components the library does
+// not implement, optimiseX on a CGp -- falls through to the inherited host implementation, call by call.
 //
 // No reference source is modified:  g++ -include gp_dropin.h gp.cpp  builds the reference's own `gp` front-end on this
 // class (build recipe and the resulting gp_l2 / gplvm_l2 executables: INTEGRATION.md, level 2).
@@ -52,8 +55,10 @@ class CGpB200 : public CGp
   void setDevice(int dev);
   // true when the next evaluation will run on the device (FTC, fixed X, every kernel component supported)
   bool onDevice() const;
+  // the same for the sparse approximations DTC / FITC / DTCVAR
+  bool onDeviceSparse() const;
   // drop the cached evaluation (call after changing *pX or *py in place without going through setOptParams/updateX)
-  void invalidate() const { state = STALE; }
+  void invalidate() const { state = STALE; sstate = STALE; }
   // device evaluations so far (one per distinct parameter point)
   unsigned long getNumDeviceEvals() const { return nEvals; }
 
@@ -69,6 +74,8 @@ class CGpB200 : public CGp
   void ensureFactored() const;  // K build + jitChol only (prediction does not need K^-1)
   void download(int which, CMatrix& dst, bool square) const;
   void fail(int rc) const;      // rc>0 -> MatrixNonPosDef, rc<0 -> Error(gpc_last_error())
+  void ensureSparseEvaluated() const; // gpc_sparse_eval
+  bool sameSparseInputs() const;
 
   mutable gpc_ctx* dev;
   mutable int64_t devN;
@@ -82,6 +89,15 @@ class CGpB200 : public CGp
   mutable double evalOut[3]; // logdet, sum_j m_j' K^-1 m_j, jitter added
   mutable std::vector<double> gNat;
   mutable unsigned long nEvals;
+  // sparse approximations
+  mutable gpc_sparse* sdev;
+  mutable int64_t sN;
+  mutable int sM, sD, sd, sApprox;
+  mutable int sstate;
+  mutable std::vector<double> skey; // kernel parameters, scales, biases, beta, X_u, m
+  mutable double spOut[6];
+  mutable std::vector<double> sgNat, sgXu;
+  mutable double sgBeta;
 };
 
 // readGpFromFile (CGp.cpp:1701-1724) for this class

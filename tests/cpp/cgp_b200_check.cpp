@@ -10,6 +10,7 @@
 //   cgp_b200_check bridge N D 0 seed kern1,kern2,... 0 [prior]   GpcKernBridge alone (host only)
 //   cgp_b200_check download N D d seed kern1,kern2,...                      CGpB200::downloadK/InvK/LcholK/Alpha through identities
 //   cgp_b200_check sparse N D d seed kern1,kern2,... approx M beta           the REFERENCE's DTC(1) / FITC(2) / DTCVAR(4) ll + gradient
+//   cgp_b200_check sparsedev N D d seed kern1,... approx M beta iters        reference CGp vs CGpB200 on a sparse approximation
 //   cgp_b200_check modelwrite N D d seed kern1,kern2,... scale prior path   the REFERENCE writes a gp model file (CGp.cpp:1640-1666)
 //   cgp_b200_check modelread 0 0 0 0 path                                   the REFERENCE reads one and prints what it holds
 //   cgp_b200_check lvmwrite N q d seed kern1,kern2,... labels 0 path        the REFERENCE writes a gplvm model file (CGplvm.cpp:761-921)
@@ -415,6 +416,77 @@ static int runSparse(unsigned int N, unsigned int D, unsigned int d, const std::
   return 0;
 }
 
+// ---- sparse approximations through the drop-in class: reference CGp and CGpB200 with the same approximation, inducing
+// inputs and beta on the same seeded data, in one process
+static int runSparseDev(unsigned int N, unsigned int D, unsigned int d, const std::string& spec, int approx, unsigned int M,
+                        double betaVal, int iters)
+{
+  CMatrix X(N, D), y(N, d);
+  for(unsigned int j = 0; j < D; j++)
+    for(unsigned int i = 0; i < N; i++)
+      X.setVal(normal01(), i, j);
+  for(unsigned int j = 0; j < d; j++)
+    for(unsigned int i = 0; i < N; i++)
+      y.setVal(sin(X.getVal(i, 0) + 0.5 * j) + 0.1 * normal01(), i, j);
+  CMatrix bias(1, d);
+  for(unsigned int j = 0; j < d; j++)
+  {
+    double sum = 0.0;
+    for(unsigned int i = 0; i < N; i++)
+      sum += y.getVal(i, j);
+    bias.setVal(sum / N, j);
+  }
+  const unsigned int Ns = 7;
+  CMatrix Xs(Ns, D);
+  for(unsigned int j = 0; j < D; j++)
+    for(unsigned int i = 0; i < Ns; i++)
+      Xs.setVal(1.2 * normal01(), i, j);
+  CCmpndKern kernRef(X), kernDev(X);
+  buildKernel(kernRef, spec, D, false);
+  buildKernel(kernDev, spec, D, false);
+  CGaussianNoise noiseRef(&y), noiseDev(&y);
+  CGp ref(&kernRef, &noiseRef, &X, approx, M, 0);
+  CGpB200 dev(&kernDev, &noiseDev, &X, approx, M, 0);
+  dev.X_u.deepCopy(ref.X_u); // CGp::initVals picks the inducing inputs at random (CGp.cpp:273-284): same ones for both
+  CGp* models[2] = {&ref, &dev};
+  for(int k = 0; k < 2; k++)
+  {
+    models[k]->setBias(bias);
+    models[k]->updateM();
+    models[k]->setBetaVal(betaVal);
+    models[k]->setDefaultOptimiser(CGp::SCG);
+  }
+  printf("{\"mode\": \"sparsedev\", \"approx\": \"%s\", \"N\": %u, \"M\": %u, \"on_device\": %d,\n",
+         ref.getApproximationStr().c_str(), N, M, dev.onDeviceSparse() ? 1 : 0);
+  CMatrix gRef(1, ref.getOptNumParams()), gDev(1, dev.getOptNumParams());
+  double llRef = models[0]->logLikelihoodGradient(gRef);
+  double llDev = models[1]->logLikelihoodGradient(gDev);
+  printf("\"ll_ref\": %.17g, \"ll_dev\": %.17g, \"ll_dev_again\": %.17g,\n", llRef, llDev, models[1]->logLikelihood());
+  printVec("g_ref", gRef);
+  printVec("g_dev", gDev);
+  unsigned long evalsAfterFirst = dev.getNumDeviceEvals();
+  CMatrix muRef(Ns, d), vRef(Ns, d), muDev(Ns, d), vDev(Ns, d);
+  ref.posteriorMeanVar(muRef, vRef, Xs);
+  dev.posteriorMeanVar(muDev, vDev, Xs);
+  printVec("out_ref", muRef);
+  printVec("out_dev", muDev);
+  printVec("std_ref", vRef);
+  printVec("std_dev", vDev);
+  if(iters > 0)
+  {
+    ref.optimise(iters);
+    dev.optimise(iters);
+    CMatrix pRef(1, ref.getOptNumParams()), pDev(1, dev.getOptNumParams());
+    ref.getOptParams(pRef);
+    dev.getOptParams(pDev);
+    printVec("opt_ref", pRef);
+    printVec("opt_dev", pDev);
+    printf("\"opt_ll_ref\": %.17g, \"opt_ll_dev\": %.17g,\n", ref.logLikelihood(), dev.logLikelihood());
+  }
+  printf("\"evals_first\": %lu, \"device_evals\": %lu}\n", evalsAfterFirst, dev.getNumDeviceEvals());
+  return 0;
+}
+
 // ---- model files: the reference as the oracle of gpc_gp_model_read / gpc_gp_model_write (tests/test_model_io_cpu.py)
 namespace
 {
@@ -662,6 +734,9 @@ int main(int argc, char** argv)
       return runDownload(N, D, d, spec);
     if(mode == "sparse") // sparse N D d seed kernels approx(1 dtc, 2 fitc, 4 dtcvar) M beta
       return runSparse(N, D, d, spec, argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 10, argc > 9 ? atof(argv[9]) : 10.0);
+    if(mode == "sparsedev") // sparsedev N D d seed kernels approx M beta iters
+      return runSparseDev(N, D, d, spec, argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 10,
+                          argc > 9 ? atof(argv[9]) : 10.0, argc > 10 ? atoi(argv[10]) : 0);
     if(mode == "modelwrite")
       return runModelWrite(N, D, d, spec, scale, prior, argc > 9 ? argv[9] : "model.txt");
     if(mode == "modelread")

@@ -346,6 +346,26 @@ int gpc_posterior(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* X
   return GPC_OK;
 }
 
+// the sparse-approximation entry points are not modelled by this test double: CGpB200 reports the error like any other
+// library failure (the device path of the sparse models is covered by the GPU tests)
+int gpc_sparse_create(gpc_sparse** out, int, int, int64_t, int, int, int)
+{
+  if(out)
+    *out = 0;
+  g_err = "mock: sparse approximations are not modelled by the test double";
+  return GPC_ERR_CUDA;
+}
+int gpc_sparse_destroy(gpc_sparse*) { return GPC_OK; }
+int gpc_sparse_set_data(gpc_sparse*, const double*, int64_t, const double*, int64_t) { return GPC_ERR_CUDA; }
+int gpc_sparse_eval(gpc_sparse*, const gpc_kcomp*, int, const double*, int64_t, double, double*, double*, double*, double*)
+{
+  return GPC_ERR_CUDA;
+}
+int gpc_sparse_posterior(gpc_sparse*, const gpc_kcomp*, int, const double*, int64_t, int64_t, double*, double*)
+{
+  return GPC_ERR_CUDA;
+}
+
 int gpc_download(gpc_ctx* c, int which, double* dst, int64_t ld)
 {
   const CMatrix* src = which == GPC_MAT_K ? &c->K : which == GPC_MAT_L ? &c->L : which == GPC_MAT_KINV ? &c->Kinv :

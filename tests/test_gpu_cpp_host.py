@@ -66,6 +66,29 @@ def test_cgp_b200_matches_reference_cgp(N, D, d, kern, scale, prior, iters):
     _assert_parity(_check("gp", N, D, d, 7, kern, scale, prior, iters), opt_tol=1e-5)
 
 
+@pytest.mark.parametrize("N,D,d,kern,approx,M,beta,iters", [
+    (300, 2, 1, "rbf,bias,white", 1, 20, 50.0, 6),      # DTC (CGp::DTC = 1), then 6 SCG iterations driven by the reference's optimiser
+    (400, 3, 2, "rbfard,white", 2, 30, 20.0, 0),        # FITC, two outputs, ARD
+    (350, 2, 1, "matern52,lin,white", 4, 25, 30.0, 0),  # DTCVAR
+    (500, 2, 1, "rbf,white", 2, 140, 10.0, 4),          # FITC with M across a tile edge
+])
+def test_cgp_b200_sparse_matches_reference_cgp(N, D, d, kern, approx, M, beta, iters):
+    """SURVEY 8(f) row 2 through the C++ host class: CGpB200 with a sparse approximation evaluates through gpc_sparse_eval /
+    gpc_sparse_posterior; ll, the optimiser-space gradient [X_u][kernel][log beta], predictions and an SCG trajectory
+    against the reference's CGp in the same process."""
+    r = _check("sparsedev", N, D, d, 5, kern, approx, M, beta, iters)
+    assert r["on_device"] == 1
+    assert r["evals_first"] == 1
+    assert _rel(r["ll_ref"], r["ll_dev"]) <= TOL
+    assert r["ll_dev"] == r["ll_dev_again"]
+    assert _rel(r["g_ref"], r["g_dev"]) <= 1e-7, (r["g_ref"], r["g_dev"])
+    assert _rel(r["out_ref"], r["out_dev"]) <= TOL
+    assert _rel(r["std_ref"], r["std_dev"]) <= TOL
+    if "opt_ref" in r:
+        assert r["opt_ll_ref"] > r["ll_ref"]
+        assert _rel(r["opt_ll_ref"], r["opt_ll_dev"]) <= 1e-5
+
+
 @pytest.mark.parametrize("N,q,d,kern,scale,prior,iters", [
     (120, 2, 5, "rbf,bias,white", 0, 0, 10),
     (200, 3, 4, "rbfard,white", 1, 0, 0),
