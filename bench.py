@@ -301,7 +301,7 @@ class ClockSampler:
         return out
 
 
-def m2_summary(N, phases, hbm_gbs, bf16_tflops, dmma_peak_tflops, slices):
+def m2_summary(N, phases, hbm_gbs, bf16_tflops, dmma_peak_tflops, slices, imma_tops=0.0):
     """BASELINE.json's second metric, "potrf + K-build GF/s vs fp64 roofline" (SURVEY.md 8(d) M2), from the phase timings
     of one evaluation: potrf counted as N^3/3 flops against (a) the fp64 DMMA pipe measured on this GPU and (b) the
     fp64-equivalent peak of the int8 tensor pipe the large products run on; K build as 8 N^2/2 bytes written against the
@@ -313,6 +313,8 @@ def m2_summary(N, phases, hbm_gbs, bf16_tflops, dmma_peak_tflops, slices):
         tf = (float(N) ** 3 / 3.0) / pt / 1e12 if pt > 0 else None
         gbs = 8.0 * float(N) ** 2 / 2.0 / kb / 1e9 if kb > 0 else None
         int8_equiv = 2.0 * float(bf16_tflops) / (slices * (slices + 1) / 2.0) if slices else None
+        if imma_tops and slices:   # the measured pipe peak when available
+            int8_equiv = float(imma_tops) / (slices * (slices + 1) / 2.0)
         out = {"potrf_tflops": tf, "potrf_gflops": tf * 1e3 if tf is not None else None,
                "potrf_frac_of_dmma_peak": tf / dmma_peak_tflops if tf and dmma_peak_tflops else None,
                "potrf_frac_of_int8_equiv_peak": tf / int8_equiv if tf and int8_equiv else None,
@@ -487,6 +489,11 @@ def main():
     check(lib().gpc_ctx_set_profile(ctx.handle, 0))
     peak = C.c_double(0)
     check(lib().gpc_bench_dmma_peak(local_rank, C.byref(peak)))
+    imma = C.c_double(0)   # measured INT8 tensor-pipe peak of this GPU (tcgen05.mma.kind::i8, TMEM/SMEM-resident loop), TOP/s
+    try:
+        check(lib().gpc_bench_imma_peak(local_rank, 4, C.byref(imma)))
+    except Exception:
+        imma = C.c_double(0)
     alg_flops = float(N) ** 3  # potrf N^3/3 + inverse 2N^3/3
     S = int(lib().gpc_gemm_engine_slices())
     traffic = None
@@ -514,15 +521,20 @@ def main():
     if oz_ms >= dm_ms and oz_ms > 0:
         # fp64-equivalent peak of the int8 pipe: int8 runs at twice the bf16 rate on sm_100a, one fp64 MMA costs
         # S(S+1)/2 = 36 int8 MMAs (S = 8 slices)
-        pk = 2.0 * bf16 / (S * (S + 1) / 2.0)
+        pk_bf16 = 2.0 * bf16 / (S * (S + 1) / 2.0)
+        pk = imma.value / (S * (S + 1) / 2.0) if imma.value > 0 else pk_bf16
         ach = oz_fl / (oz_ms * 1e-3) / 1e12
         roofline = {
             "bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma.kind::i8 + TMEM + TMA; fp64 via %d int8 slices) incl. slicing" % S,
             "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
             "traffic": ((traffic or {}).get("oz_gemm_kernel") or {}).get("dram_bytes_per_launch"),
             "traffic_note": "ncu --set full, SYRK-shaped call n=8192 k=4096 (profiles/oz_gemm_kernel_ncu_r01.txt); algorithmic bytes of that launch: %s" % ((traffic or {}).get("oz_gemm_kernel") or {}).get("algorithmic_bytes"),
-            "peak_source": "fp64-equivalent of the int8 tensor pipe: 2 x %s = %.0f TOP/s, / S(S+1)/2 int8 MMAs per fp64 MMA; "
-                           "of measured" % (bf16_src, 2.0 * bf16),
+            "peak_source": ("fp64-equivalent of the int8 tensor pipe MEASURED on this GPU in this run (gpc_bench_imma_peak: "
+                            "tcgen05.mma.kind::i8 M128 N256 K32 on SMEM-resident operands, %.0f TOP/s) / S(S+1)/2 = %d int8 MMAs "
+                            "per fp64 MMA" % (imma.value, S * (S + 1) // 2)) if imma.value > 0 else
+                           "fp64-equivalent of 2 x %s (imma peak measurement failed)" % bf16_src,
+            "int8_peak_tops_measured": imma.value,
+            "peak_from_2x_bf16": pk_bf16, "frac_of_2x_bf16_peak": ach / pk_bf16,
             "int8_mmas_per_fp64_mma": S * (S + 1) // 2,
             "launches_per_eval": oz_n, "kernel_ms_per_eval": oz_ms, "algorithmic_flops": oz_fl,
             "share_of_step": oz_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
@@ -632,7 +644,7 @@ def main():
             "kbuild_gbs": 8.0 * N * N / 2 / (phases["kbuild"] * 1e-3) / 1e9,
             "kbuild_bytes_written": int(8 * N * N // 2),
             "kbuild_gbs_full_matrix_equiv": 8.0 * N * N / (phases["kbuild"] * 1e-3) / 1e9,
-            "m2": m2_summary(N, phases, mp.get("hbm_gbs"), bf16, peak.value, S),
+            "m2": m2_summary(N, phases, mp.get("hbm_gbs"), bf16, peak.value, S, imma.value),
             "also": also,
             "sharded": sharded,
         }

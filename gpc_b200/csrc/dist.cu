@@ -373,8 +373,47 @@ static int diag_factor(DistRank& r, int k) {
 }
 
 // K -> K^-1 in place (see the file header).  Everything is queued; the caller synchronises.
+struct SweepProf {  // GPC_DIST_PROFILE=1: per-stage durations of the sweep (timing events on the stage's own stream)
+  std::vector<cudaEvent_t> ev;
+  int nbt = 0;
+  cudaEvent_t at(int k, int i) { return ev[(size_t)k * 8 + i]; }
+};
+static SweepProf* sweep_prof(int nbt) {
+  static thread_local SweepProf* p = nullptr;
+  static int on = -1;
+  if (on < 0) on = getenv("GPC_DIST_PROFILE") ? 1 : 0;
+  if (!on) return nullptr;
+  if (!p) p = new SweepProf();
+  if (p->nbt < nbt) {
+    size_t old = p->ev.size();
+    p->ev.resize((size_t)nbt * 8);
+    for (size_t i = old; i < p->ev.size(); i++) cudaEventCreate(&p->ev[i]);
+    p->nbt = nbt;
+  }
+  return p;
+}
+static void sweep_prof_report(SweepProf* pf, int nbt) {
+  if (!pf) return;
+  const char* names[] = {"lookahead strips", "diag factor", "W bcast wait", "panel products + slicing", "slot bcast", "bulk update"};
+  const int a[] = {0, 1, 2, 3, 4, 6}, b[] = {1, 2, 3, 4, 5, 7};
+  double chain = 0.0;
+  for (int st = 0; st < 6; st++) {
+    double tot = 0.0;
+    for (int k = 0; k < nbt; k++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pf->at(k, a[st]), pf->at(k, b[st])) == cudaSuccess) tot += ms;
+    }
+    fprintf(stderr, "[gpc dist profile] %-26s total %8.3f ms  (%.3f ms / step)\n", names[st], tot, tot / nbt);
+    if (st < 5) chain += tot;
+  }
+  fprintf(stderr, "[gpc dist profile] chain (panel + comm streams) %.3f ms, %d steps\n", chain, nbt);
+}
+
 static int sweep(DistRank& r) {
   const int nb = r.nb, NBt = r.NBt, P = r.P, Q = r.Q, p = r.p, q = r.q;
+  SweepProf* pf = (r.rank == 0) ? sweep_prof(NBt) : nullptr;
+#define PROF(k, i, stream) \
+  if (pf) GPC_CUDA_CHECK(cudaEventRecord(pf->at(k, i), stream))
   const OzCycGrid gr{P, Q, p, q};
   const size_t sb = oz_slot_bytes(nb, r.S);
   std::vector<BcastItem> items((size_t)NBt);
@@ -385,6 +424,7 @@ static int sweep(DistRank& r) {
     // ---- look-ahead: block column k and block row k receive the update of panel k-1 ahead of the bulk
     if (k >= 1) GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, EV(0, k - 1), 0));
     if (k >= 2) GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, EV(1, k - 2), 0));
+    PROF(k, 0, r.s_panel);
     if (k >= 1) {
       if (col_owner) {
         const int64_t r0 = (int64_t)r.lrow_lb(k) * nb;
@@ -398,7 +438,9 @@ static int sweep(DistRank& r) {
       }
     }
     // ---- diagonal block: L_kk (in place) and W_kk = L_kk^-1, then W_kk to everybody
+    PROF(k, 1, r.s_panel);
     if (diag_owner) GPC_CHECK(diag_factor(r, k));
+    PROF(k, 2, r.s_panel);
     GPC_CUDA_CHECK(cudaEventRecord(EV(2, k), r.s_panel));
     GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_comm, EV(2, k), 0));
     {
@@ -407,6 +449,7 @@ static int sweep(DistRank& r) {
     }
     GPC_CUDA_CHECK(cudaEventRecord(EV(3, k), r.s_comm));
     GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, EV(3, k), 0));
+    PROF(k, 3, r.s_panel);
     // ---- this rank's blocks of panel k, sliced straight into their slots
     if (col_owner) {  // L_ik = A_ik W_kk'  for the local block rows with global index > k
       const int il0 = r.lrow_lb(k + 1);
@@ -430,17 +473,21 @@ static int sweep(DistRank& r) {
     }
     if (diag_owner)  // S_k = W_kk'
       GPC_CHECK(oz_slice_to_slots(r.Wb, nb, true, nb, nb, r.S, r.emax, r.slots[b], k, 0, r.s_panel, &r.launches));
+    PROF(k, 4, r.s_panel);
     GPC_CUDA_CHECK(cudaEventRecord(EV(4, k), r.s_panel));
     // ---- the panel to everybody: one broadcast per slot, from the rank that produced it
     GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_comm, EV(4, k), 0));
     for (int g = 0; g < NBt; g++) items[(size_t)g] = BcastItem{r.slots[b] + (size_t)g * sb, sb, r.producer(g, k)};
     GPC_CHECK(r.comm->bcast_group(items.data(), NBt, r.s_comm));
+    PROF(k, 5, r.s_comm);
     GPC_CUDA_CHECK(cudaEventRecord(EV(0, k), r.s_comm));
     // ---- bulk update of step k: every local block except block row / column k+1 (done by the look-ahead of step k+1)
     GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_main, EV(0, k), 0));
     const int skip = (k + 1 < NBt) ? k + 1 : -1;
+    PROF(k, 6, r.s_main);
     GPC_CHECK(launch_oz_cyc_update(r.maps[b], gr, k, skip, skip, r.T, r.ML, 0, r.ML, 0, r.NL, r.errflag, r.s_main,
                                    &r.launches));
+    PROF(k, 7, r.s_main);
     GPC_CUDA_CHECK(cudaEventRecord(EV(1, k), r.s_main));
   }
   // the other two streams have nothing queued beyond what the main stream already waited for, except the last panel's
@@ -451,6 +498,11 @@ static int sweep(DistRank& r) {
   e = r.ev[(size_t)5 * NBt + 1];
   GPC_CUDA_CHECK(cudaEventRecord(e, r.s_comm));
   GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_main, e, 0));
+#undef PROF
+  if (pf) {
+    GPC_CUDA_CHECK(cudaStreamSynchronize(r.s_main));
+    sweep_prof_report(pf, NBt);
+  }
   return GPC_OK;
 }
 

@@ -942,6 +942,113 @@ int launch_oz_cyc_update(const OzCycMaps& maps, const OzCycGrid& gr, int kstep, 
   return GPC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Measured peak of the INT8 tensor pipe (the denominator of the engine's roofline): one CTA per SM keeps issuing
+// tcgen05.mma.kind::i8 M = 128, N = 256, K = 32 on shared-memory-resident operands (no TMA, no epilogue) into its 512
+// TMEM columns.  Two variants: every instruction reads fresh A and B from shared memory exactly like the GEMM kernel's
+// widest instruction (12 KB per 1.05 M MACs); ops = CTAs x instructions x 2 x 128 x 256 x 32.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OZ_THREADS, 1) oz_imma_peak_kernel(int iters, int nwide, int* errflag) {
+  extern __shared__ uint8_t oz_smem_raw[];
+  const uint32_t raw = smem_u32(oz_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = oz_smem_raw + (base - raw);
+  const uint32_t sA = base;                         // 16 KB: 128 rows x 128 B
+  const uint32_t sB = base + OZ_A_BYTES;            // 32 KB: 256 rows x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + OZ_A_BYTES + 4 * OZ_B_BYTES);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + OZ_A_BYTES + 4 * OZ_B_BYTES + 64);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < (OZ_A_BYTES + 4 * OZ_B_BYTES) / 4; i += OZ_THREADS) reinterpret_cast<uint32_t*>(gbase)[i] = 0x01010101u;
+  const uint32_t bar0 = smem_u32(bars);
+  if (warp == 4 && lane == 0) {
+    oz_mbar_init(bar0, 1);
+    oz_mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  oz_tc_fence_before();
+  __syncthreads();
+  oz_tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  if (warp == 5) {
+    const uint32_t a_lo = oz_desc_lo(sA), b_lo = oz_desc_lo(sB);
+    const int n = nwide * OZ_BN;  // 64 .. 256
+    uint32_t ph[2] = {0, 0};
+    for (int it = 0; it < iters; it++) {
+      const int half = it & 1;
+      if (it >= 2) {  // at most two batches in flight
+        oz_mbar_wait(bar0 + 8 * half, ph[half], errflag, 9);
+        ph[half] ^= 1;
+      }
+      oz_tc_fence_after();
+      if (oz_elect_one()) {
+#pragma unroll
+        for (int rep = 0; rep < 8; rep++)
+#pragma unroll
+          for (int ks = 0; ks < OZ_BK / OZ_UK; ks++)
+            oz_mma_i8_lo(tmem + (uint32_t)half * 256, a_lo + ks * (OZ_UK >> 4), b_lo + ks * (OZ_UK >> 4), oz_idesc_c(n),
+                         (it >= 2 || rep || ks) ? 1u : 0u);
+        oz_tc_commit(bar0 + 8 * half);
+      }
+      __syncwarp();
+    }
+    for (int half = 0; half < 2; half++)
+      if (iters > half) oz_mbar_wait(bar0 + 8 * half, ph[half], errflag, 10);
+  }
+  oz_tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    oz_tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+int oz_bench_imma_peak(int device, int nwide, double* tops) {
+  GPC_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GPC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (nwide < 1 || nwide > 4) nwide = 4;
+  const size_t smem = 1024 + OZ_A_BYTES + 4 * OZ_B_BYTES + 256;
+  GPC_CUDA_CHECK(cudaFuncSetAttribute(oz_imma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int* err = nullptr;
+  GPC_CUDA_CHECK(cudaMalloc(&err, sizeof(int)));
+  GPC_CUDA_CHECK(cudaMemset(err, 0, sizeof(int)));
+  cudaStream_t s;
+  GPC_CUDA_CHECK(cudaStreamCreate(&s));
+  cudaEvent_t e0, e1;
+  GPC_CUDA_CHECK(cudaEventCreate(&e0));
+  GPC_CUDA_CHECK(cudaEventCreate(&e1));
+  const int ctas = prop.multiProcessorCount, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    GPC_CUDA_CHECK(cudaEventRecord(e0, s));
+    oz_imma_peak_kernel<<<ctas, OZ_THREADS, smem, s>>>(iters, nwide, err);
+    GPC_CUDA_CHECK(cudaEventRecord(e1, s));
+    GPC_CUDA_CHECK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double ops = (double)ctas * iters * 8.0 * (OZ_BK / OZ_UK) * 2.0 * OZ_BM * (double)(nwide * OZ_BN) * OZ_UK;
+    const double t = ops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && t > best) best = t;
+  }
+  int herr = 0;
+  cudaMemcpy(&herr, err, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(err);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(s);
+  if (herr) {
+    set_error("oz_bench_imma_peak: pipeline protocol error");
+    return GPC_ERR_CUDA;
+  }
+  if (tops) *tops = best;
+  return GPC_OK;
+}
+
 void oz_release_device(int dev) {
   if (dev < 0 || dev >= 64) return;
   std::lock_guard<std::mutex> lk(g_oz_mu);
@@ -970,6 +1077,9 @@ void oz_release_device(int dev) {
 }
 
 }  // namespace gpc
+
+// measured INT8 tensor-pipe peak of this device in TOP/s (ops = 2 x MACs); nwide = N / 64 of the instruction (1..4)
+extern "C" int gpc_bench_imma_peak(int device, int nwide, double* tops) { return gpc::oz_bench_imma_peak(device, nwide, tops); }
 
 extern "C" int gpc_oz_slice_check(int device, int64_t R, int64_t K, int kc, int S, const double* X, signed char* slices_out,
                                   double* scale_out) {

@@ -247,6 +247,10 @@ int gpc_dist_plan(int P, int Q, int rank, int64_t N, int nb, int k, int* out12, 
 /* ---- measurement helpers (bench.py) ----------------------------------------------------------------- */
 /* register-resident DMMA loop: measured fp64 tensor-pipe peak of this device in TFLOP/s */
 int gpc_bench_dmma_peak(int device, double* tflops);
+/* the same for the INT8 tensor pipe the large fp64 products run on (ozaki.cu): one CTA per SM issuing tcgen05.mma.kind::i8
+ * M = 128, N = 64 nwide (nwide 1..4), K = 32 on shared-memory-resident operands into TMEM; *tops = 2 x MACs / s / 1e12.
+ * The fp64-equivalent peak of the engine is tops / (S (S + 1) / 2) for S slices (36 int8 MMAs per fp64 MMA at S = 8). */
+int gpc_bench_imma_peak(int device, int nwide, double* tops);
 /* C(n x n) -= A(n x k) A' (lower) on device scratch: the SYRK trailing update in isolation.  *ms per launch */
 int gpc_bench_syrk(int device, int64_t n, int64_t k, int reps, double* ms);
 /* the 128 x 128 diagonal-block kernel (Cholesky + inverse of the factor, N/128 times on the critical path) in
