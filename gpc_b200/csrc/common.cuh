@@ -87,7 +87,7 @@ size_t oz_slot_bytes(int nb, int S);   // bytes of one slot: S planes of nb x nb
 int oz_slice_to_slots(const double* g, int64_t ld, bool kc, int64_t R, int nb, int S, int* emax_scratch, uint8_t* slots,
                       int slot0, int slot_stride, cudaStream_t s, int64_t* launches);
 int oz_cyc_maps(OzCycMaps* out, const uint8_t* slots, int nslots, int nb, int S);
-int launch_oz_cyc_update(const OzCycMaps& maps, const OzCycGrid& gr, int kstep, int skip_i, int skip_j, double* C,
+int launch_oz_cyc_update(const OzCycMaps& maps, const OzCycGrid& gr, int kstep, int skip_lo, int skip_hi, double* C,
                          int64_t ldc, int64_t r0, int64_t m, int64_t c0, int64_t n, int* errflag, cudaStream_t s,
                          int64_t* launches);
 

@@ -251,6 +251,8 @@ struct DistRank {
   int64_t ML = 0, NL = 0;    // local matrix
   double *X = nullptr, *M = nullptr, *alpha = nullptr, *y = nullptr, *T = nullptr;
   double *Wb = nullptr, *Lp = nullptr, *tmpL = nullptr, *Tpool = nullptr;
+  double *Wb2 = nullptr, *LF[2] = {nullptr, nullptr};  // single-rank fast chain: second W_kk buffer, the fp64 tiles L_{k+1,k}
+  cudaStream_t s_chain = nullptr;
   int* emax = nullptr;
   uint8_t* slots[2] = {nullptr, nullptr};
   OzCycMaps maps[2];
@@ -306,6 +308,11 @@ static int rank_alloc(DistRank& r) {
   if (r.ML > 0 && r.NL > 0) GPC_CUDA_CHECK(cudaMalloc(&r.T, (size_t)r.ML * (size_t)r.NL * sizeof(double)));
   GPC_CUDA_CHECK(cudaMalloc(&r.Wb, nb * nb * sizeof(double)));
   GPC_CUDA_CHECK(cudaMemset(r.Wb, 0, nb * nb * sizeof(double)));
+  if (r.world == 1) {
+    GPC_CUDA_CHECK(cudaMalloc(&r.Wb2, nb * nb * sizeof(double)));
+    GPC_CUDA_CHECK(cudaMemset(r.Wb2, 0, nb * nb * sizeof(double)));
+    for (int b = 0; b < 2; b++) GPC_CUDA_CHECK(cudaMalloc(&r.LF[b], nb * nb * sizeof(double)));
+  }
   const size_t strip = (size_t)(r.ML > r.NL ? r.ML : r.NL) + nb;
   GPC_CUDA_CHECK(cudaMalloc(&r.Lp, strip * nb * sizeof(double)));
   GPC_CUDA_CHECK(cudaMalloc(&r.emax, strip * sizeof(int)));
@@ -328,7 +335,8 @@ static int rank_alloc(DistRank& r) {
   GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_main, cudaStreamNonBlocking, lo));
   GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_panel, cudaStreamNonBlocking, hi));
   GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_comm, cudaStreamNonBlocking, hi));
-  r.ev.resize((size_t)5 * r.NBt + 8);
+  GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_chain, cudaStreamNonBlocking, hi));
+  r.ev.resize((size_t)8 * r.NBt + 8);
   for (auto& e : r.ev) GPC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int i = 0; i < 6; i++) GPC_CUDA_CHECK(cudaEventCreate(&r.tev[i]));
   return GPC_OK;
@@ -339,6 +347,8 @@ static void rank_free(DistRank& r) {
   if (r.s_main) cudaStreamSynchronize(r.s_main);
   if (r.s_panel) cudaStreamSynchronize(r.s_panel);
   if (r.s_comm) cudaStreamSynchronize(r.s_comm);
+  if (r.s_chain) cudaStreamSynchronize(r.s_chain);
+  cudaFree(r.Wb2); cudaFree(r.LF[0]); cudaFree(r.LF[1]);
   cudaFree(r.X); cudaFree(r.M); cudaFree(r.alpha); cudaFree(r.y); cudaFree(r.T); cudaFree(r.Wb); cudaFree(r.Lp);
   cudaFree(r.emax); cudaFree(r.tmpL); cudaFree(r.Tpool); cudaFree(r.slots[0]); cudaFree(r.slots[1]); cudaFree(r.scal);
   cudaFree(r.info); cudaFree(r.errflag); cudaFree(r.partial);
@@ -350,13 +360,15 @@ static void rank_free(DistRank& r) {
   if (r.s_main) cudaStreamDestroy(r.s_main);
   if (r.s_panel) cudaStreamDestroy(r.s_panel);
   if (r.s_comm) cudaStreamDestroy(r.s_comm);
+  if (r.s_chain) cudaStreamDestroy(r.s_chain);
 }
 
 // Cholesky of the diagonal block (k, k) in place + its inverse into Wb: the single-GPU recursion on one nb x nb block
-static int diag_factor(DistRank& r, int k) {
+static int diag_factor(DistRank& r, int k, cudaStream_t stream = nullptr, double* Wout = nullptr) {
   const int64_t gb = (int64_t)k * r.nb;
+  if (!Wout) Wout = r.Wb;
   Dense d;
-  d.s = r.s_panel;
+  d.s = stream ? stream : r.s_panel;
   d.launches = &r.launches;
   d.Dinv = nullptr;
   d.info = r.info;
@@ -364,7 +376,7 @@ static int diag_factor(DistRank& r, int k) {
   d.W = nullptr;
   d.nvalid = r.N;
   d.ldw = r.nb;
-  d.Winv = r.Wb - (gb + gb * d.ldw);  // potrf_inv_rec addresses W by the block's global position
+  d.Winv = Wout - (gb + gb * d.ldw);  // potrf_inv_rec addresses W by the block's global position
   d.tmpL = r.tmpL;
   d.Tpool = r.Tpool;
   d.TLpool = nullptr;
@@ -492,16 +504,137 @@ static int sweep(DistRank& r) {
   }
   // the other two streams have nothing queued beyond what the main stream already waited for, except the last panel's
   // producers: join them
-  cudaEvent_t e = r.ev[(size_t)5 * NBt];
+  cudaEvent_t e = r.ev[(size_t)8 * NBt];
   GPC_CUDA_CHECK(cudaEventRecord(e, r.s_panel));
   GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_main, e, 0));
-  e = r.ev[(size_t)5 * NBt + 1];
+  e = r.ev[(size_t)8 * NBt + 1];
   GPC_CUDA_CHECK(cudaEventRecord(e, r.s_comm));
   GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_main, e, 0));
 #undef PROF
   if (pf) {
     GPC_CUDA_CHECK(cudaStreamSynchronize(r.s_main));
     sweep_prof_report(pf, NBt);
+  }
+  return GPC_OK;
+}
+
+// Single rank: the same sweep with the critical path cut down to what it really is.  The next diagonal block needs only
+// ONE block of the current panel -- T_{k+1,k+1} -= L_{k+1,k} L_{k+1,k}' -- so a dedicated chain stream does
+//     T_kk -= L_{k,k-1} L_{k,k-1}'  ->  potrf + inverse of T_kk  ->  L_{k+1,k} = T_{k+1,k} W_kk'        (fp64, one block each)
+// while the rest of panel k (all block rows, slicing), the look-ahead strips and the bulk update run behind it on the
+// panel / main streams.  (With several ranks block (k+1, k) and block (k+1, k+1) live on different GPUs in general.)
+static int sweep_solo(DistRank& r) {
+  const int nb = r.nb, NBt = r.NBt;
+  const OzCycGrid gr{1, 1, 0, 0};
+  // events: 0 slots ready, 1 step k applied to block row / column k+2 (second look-ahead, first thing on the main stream),
+  //         2 W_kk ready, 3 look-ahead strips done, 4 L_{k+1,k} ready, 5 bulk update of step k done
+  auto EV = [&](int kind, int k) { return r.ev[(size_t)kind * NBt + k]; };
+  SweepProf* pf = sweep_prof(NBt);
+#define PROF(k, i, stream) \
+  if (pf) GPC_CUDA_CHECK(cudaEventRecord(pf->at(k, i), stream))
+  {  // the chain stream starts after whatever the panel stream was told to wait for (the K build)
+    cudaEvent_t e = r.ev[(size_t)8 * NBt + 3];
+    GPC_CUDA_CHECK(cudaEventRecord(e, r.s_panel));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_chain, e, 0));
+  }
+  for (int k = 0; k < NBt; k++) {
+    const int b = k & 1;
+    double* Wk = b ? r.Wb2 : r.Wb;
+    double* Tkk = r.T + (int64_t)k * nb + (int64_t)k * nb * r.ML;
+    // ---- panel stream: panel k-1 applied to block column k (rows > k) and block row k (columns < k)
+    PROF(k, 0, r.s_panel);
+    if (k >= 1) {
+      GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, EV(0, k - 1), 0));
+      if (k >= 2) GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, EV(1, k - 2), 0));
+      GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, EV(4, k - 1), 0));  // the chain has read T_{k,k-1}
+      const int64_t r0 = (int64_t)(k + 1) * nb;
+      GPC_CHECK(launch_oz_cyc_update(r.maps[(k - 1) & 1], gr, k - 1, -1, -1, r.T, r.ML, r0, r.ML - r0, (int64_t)k * nb, nb,
+                                     r.errflag, r.s_panel, &r.launches));
+      GPC_CHECK(launch_oz_cyc_update(r.maps[(k - 1) & 1], gr, k - 1, -1, -1, r.T, r.ML, (int64_t)k * nb, nb, 0,
+                                     (int64_t)k * nb, r.errflag, r.s_panel, &r.launches));
+    }
+    GPC_CUDA_CHECK(cudaEventRecord(EV(3, k), r.s_panel));
+    PROF(k, 1, r.s_panel);
+    // ---- chain stream: the diagonal block
+    if (k >= 2) GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_chain, EV(1, k - 2), 0));
+    PROF(k, 2, r.s_chain);
+    if (k >= 1) {
+      double* Lf = r.LF[(k - 1) & 1];
+      GemmCall g{Lf, Lf, Tkk, nb, nb, r.ML, nb, nb, nb, -1.0, 1.0, false, false, true};
+      GPC_CHECK(launch_gemm(g, r.s_chain, &r.launches));
+    }
+    GPC_CHECK(diag_factor(r, k, r.s_chain, Wk));
+    GPC_CUDA_CHECK(cudaEventRecord(EV(2, k), r.s_chain));
+    PROF(k, 3, r.s_chain);
+    if (k + 1 < NBt) {  // L_{k+1,k} for the next diagonal block
+      GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_chain, EV(3, k), 0));
+      GemmCall g{r.T + (int64_t)(k + 1) * nb + (int64_t)k * nb * r.ML, Wk, r.LF[b], r.ML, nb, nb, nb, nb, nb, 1.0, 0.0, false,
+                 false, false};
+      g.b_tri = -1;
+      GPC_CHECK(launch_gemm(g, r.s_chain, &r.launches));
+    }
+    GPC_CUDA_CHECK(cudaEventRecord(EV(4, k), r.s_chain));
+    PROF(k, 4, r.s_chain);
+    // ---- panel stream: the whole panel k, sliced into its slots (free once the bulk update of step k-2 has read them)
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, EV(2, k), 0));
+    if (k >= 2) GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, EV(5, k - 2), 0));
+    PROF(k, 5, r.s_panel);
+    {
+      const int64_t m = r.ML - (int64_t)(k + 1) * nb;
+      if (m > 0) {
+        GemmCall g{r.T + (int64_t)(k + 1) * nb + (int64_t)k * nb * r.ML, Wk, r.Lp, r.ML, nb, m, m, nb, nb, 1.0, 0.0, false, false,
+                   false};
+        g.b_tri = -1;
+        GPC_CHECK(launch_gemm(g, r.s_panel, &r.launches));
+        GPC_CHECK(oz_slice_to_slots(r.Lp, m, false, m, nb, r.S, r.emax, r.slots[b], k + 1, 1, r.s_panel, &r.launches));
+      }
+      const int64_t mr = (int64_t)k * nb;
+      if (mr > 0) {
+        GemmCall g{r.T + (int64_t)k * nb, Wk, r.Lp, r.ML, nb, mr, mr, nb, nb, 1.0, 0.0, true, false, false};
+        g.b_tri = -1;
+        GPC_CHECK(launch_gemm(g, r.s_panel, &r.launches));
+        GPC_CHECK(oz_slice_to_slots(r.Lp, mr, false, mr, nb, r.S, r.emax, r.slots[b], 0, 1, r.s_panel, &r.launches));
+      }
+      GPC_CHECK(oz_slice_to_slots(Wk, nb, true, nb, nb, r.S, r.emax, r.slots[b], k, 0, r.s_panel, &r.launches));
+    }
+    GPC_CUDA_CHECK(cudaEventRecord(EV(0, k), r.s_panel));
+    PROF(k, 6, r.s_panel);
+    // ---- main stream: bulk update of step k (everything but block row / column k+1), after the chain has read T_{k+1,k}
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_main, EV(0, k), 0));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_main, EV(4, k), 0));
+    if (k + 2 < NBt) {  // second look-ahead: block column k+2 (rows >= k+2) and block row k+2 (columns <= k) first ...
+      const int64_t c2 = (int64_t)(k + 2) * nb;
+      GPC_CHECK(launch_oz_cyc_update(r.maps[b], gr, k, -1, -1, r.T, r.ML, c2, r.ML - c2, c2, nb, r.errflag, r.s_main,
+                                     &r.launches));
+      GPC_CHECK(launch_oz_cyc_update(r.maps[b], gr, k, -1, -1, r.T, r.ML, c2, nb, 0, (int64_t)(k + 1) * nb, r.errflag, r.s_main,
+                                     &r.launches));
+    }
+    GPC_CUDA_CHECK(cudaEventRecord(EV(1, k), r.s_main));
+    {  // ... then everything else (block rows / columns k+1 and k+2 left out)
+      const int lo = (k + 1 < NBt) ? k + 1 : -1, hi = (k + 2 < NBt) ? k + 2 : k + 1;
+      GPC_CHECK(launch_oz_cyc_update(r.maps[b], gr, k, lo, hi, r.T, r.ML, 0, r.ML, 0, r.NL, r.errflag, r.s_main, &r.launches));
+    }
+    GPC_CUDA_CHECK(cudaEventRecord(EV(5, k), r.s_main));
+  }
+  cudaEvent_t e = r.ev[(size_t)8 * NBt];
+  GPC_CUDA_CHECK(cudaEventRecord(e, r.s_panel));
+  GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_main, e, 0));
+  e = r.ev[(size_t)8 * NBt + 1];
+  GPC_CUDA_CHECK(cudaEventRecord(e, r.s_chain));
+  GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_main, e, 0));
+#undef PROF
+  if (pf) {
+    GPC_CUDA_CHECK(cudaStreamSynchronize(r.s_main));
+    const char* names[] = {"look-ahead strips", "chain: SYRK + diag factor", "chain: L(k+1,k)", "panel products + slicing"};
+    const int a[] = {0, 2, 3, 5}, bb[] = {1, 3, 4, 6};
+    for (int st = 0; st < 4; st++) {
+      double tot = 0.0;
+      for (int k = 0; k < NBt; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pf->at(k, a[st]), pf->at(k, bb[st])) == cudaSuccess) tot += ms;
+      }
+      fprintf(stderr, "[gpc sweep profile] %-28s total %8.3f ms  (%.3f ms / step)\n", names[st], tot, tot / NBt);
+    }
   }
   return GPC_OK;
 }
@@ -532,12 +665,13 @@ static int rank_eval(DistRank& r, const KSpec& ks, EvalOut* out) {
     GPC_CHECK(launch_kbuild_cyc(ks, r.X, r.Np, r.N, r.T, r.ML, cm, jitter_used, s, &r.launches));
     GPC_CUDA_CHECK(cudaEventRecord(r.tev[1], s));
     {  // the panel stream starts after the K build
-      cudaEvent_t e = r.ev[(size_t)5 * r.NBt + 2];
+      cudaEvent_t e = r.ev[(size_t)8 * r.NBt + 2];
       GPC_CUDA_CHECK(cudaEventRecord(e, s));
       GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, e, 0));
       GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_comm, e, 0));
     }
-    GPC_CHECK(sweep(r));
+    if (r.world == 1 && !getenv("GPC_SWEEP_GENERIC")) GPC_CHECK(sweep_solo(r));
+    else GPC_CHECK(sweep(r));
     GPC_CUDA_CHECK(cudaEventRecord(r.tev[2], s));
     // alpha = K^-1 m: local symmetric block product, all-reduce
     GPC_CUDA_CHECK(cudaMemsetAsync(r.y, 0, (size_t)r.Np * r.d * sizeof(double), s));

@@ -273,13 +273,13 @@ struct OzArgs {
   // ---- block-cyclic one-sweep mode (dist.cu): C is the LOCAL part of a matrix distributed in nb x nb blocks over a
   // P x Q process grid (local block (il, jl) = global block (il P + p, jl Q + q)); both operands are block rows of ONE
   // pre-sliced panel held in "slots" (slot g = global block g: S planes of nb x nb int8, then nb row scales).  Per tile:
-  //   skipped unless global block row >= global block column (and != skip_i / skip_j);
+  //   skipped unless global block row >= global block column (and neither lies in [skip_lo, skip_hi]);
   //   C = beta' C + alpha' A B',  alpha' = -1 below the panel's step row (i > kstep), +1 at / above it,
   //                               beta' = 0 in block row kstep and block column kstep, 1 elsewhere.
   int cyc;               // 0: off
   int nb, P, Q, p, q;    // block size (multiple of 128) and grid position
   int kstep;             // global block index of the current panel
-  int skip_i, skip_j;    // global block row / column left out (-1: none): done by a separate (look-ahead) launch
+  int skip_lo, skip_hi;  // global block rows AND columns in [skip_lo, skip_hi] are left out (-1, -1: none): look-ahead launches
   int bm0, bn0;          // tile offsets of the launched sub-rectangle inside the local matrix
   int slot_rows;         // rows (of nb bytes) per slot = S * nb + 8
   const uint8_t* slots;  // base of the slot buffer (for the row scales)
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     bn += a.bn0;
     const int il = (bm * OZ_BM) / a.nb, jl = (bn * OZ_BN) / a.nb;
     const int gi = il * a.P + a.p, gj = jl * a.Q + a.q;
-    if (gi < gj || gi == a.skip_i || gj == a.skip_j) return;
+    if (gi < gj || (gi >= a.skip_lo && gi <= a.skip_hi) || (gj >= a.skip_lo && gj <= a.skip_hi)) return;
     const int ri = bm * OZ_BM - il * a.nb, rj = bn * OZ_BN - jl * a.nb;
     a_row0 = gi * a.slot_rows + ri;
     b_row0 = gj * a.slot_rows + rj;
@@ -880,7 +880,7 @@ int oz_cyc_maps(OzCycMaps* out, const uint8_t* slots, int nslots, int nb, int S)
 
 // C (local part, ld ldc) updated with the panel in `maps` over the tile sub-rectangle rows [r0, r0 + m), columns
 // [c0, c0 + n) of the local matrix (multiples of 128 / 64); see OzArgs for the per-tile rule.
-int launch_oz_cyc_update(const OzCycMaps& maps, const OzCycGrid& gr, int kstep, int skip_i, int skip_j, double* C,
+int launch_oz_cyc_update(const OzCycMaps& maps, const OzCycGrid& gr, int kstep, int skip_lo, int skip_hi, double* C,
                          int64_t ldc, int64_t r0, int64_t m, int64_t c0, int64_t n, int* errflag, cudaStream_t s,
                          int64_t* launches) {
   if (m <= 0 || n <= 0) return GPC_OK;
@@ -912,8 +912,8 @@ int launch_oz_cyc_update(const OzCycMaps& maps, const OzCycGrid& gr, int kstep, 
   a.p = gr.p;
   a.q = gr.q;
   a.kstep = kstep;
-  a.skip_i = skip_i;
-  a.skip_j = skip_j;
+  a.skip_lo = skip_lo < 0 ? 0x7fffffff : skip_lo;  // empty range when there is nothing to leave out
+  a.skip_hi = skip_lo < 0 ? -1 : skip_hi;
   a.bm0 = (int)(r0 / OZ_BM);
   a.bn0 = (int)(c0 / OZ_BN);
   a.slot_rows = S * nb + 8;
