@@ -71,7 +71,7 @@ SYMBOLS = [
     "gpc_kern_build", "gpc_kern_cross", "gpc_kern_diag", "gpc_add_diag", "gpc_potrf", "gpc_jitchol",
     "gpc_solve_alpha", "gpc_inverse", "gpc_alpha_from_inverse", "gpc_grad", "gpc_kern_grad", "gpc_kern_grad_cross", "gpc_posterior",
     "gpc_eval", "gpc_download", "gpc_last_timings", "gpc_last_enqueue_ms", "gpc_dpotrf", "gpc_dpotri", "gpc_dtrsm", "gpc_dsyrk",
-    "gpc_dgemm", "gpc_dsymv", "gpc_bench_dmma_peak", "gpc_bench_imma_peak", "gpc_bench_syrk", "gpc_ctx_set_profile", "gpc_last_gemm_profile", "gpc_last_gemm_profile_split", "gpc_bench_gemm",
+    "gpc_dgemm", "gpc_dsymv", "gpc_dsyr", "gpc_bench_dmma_peak", "gpc_bench_imma_peak", "gpc_bench_syrk", "gpc_ctx_set_profile", "gpc_last_gemm_profile", "gpc_last_gemm_profile_split", "gpc_bench_gemm",
     "gpc_bench_leaf", "gpc_ctx_dims", "gpc_gp_optimise_scg", "gpc_scg_minimise", "gpc_svml_dims", "gpc_svml_read", "gpc_set_gemm_engine", "gpc_gemm_engine_slices", "gpc_gemm_check", "gpc_oz_slice_check",
     "gpc_gp_model_read", "gpc_gp_model_write", "gpc_gp_model_check_roundtrip", "gpc_gplvm_model_read",
     "gpc_gplvm_model_write",
@@ -134,6 +134,7 @@ def lib():
                             C.c_void_p, i64]
     L.gpc_dgemm.argtypes = [C.c_int, C.c_char, C.c_char, i64, i64, i64, C.c_double, C.c_void_p, i64, C.c_void_p, i64,
                             C.c_double, C.c_void_p, i64]
+    L.gpc_dsyr.argtypes = [C.c_int, C.c_char, i64, C.c_double, C.c_void_p, i64, C.c_void_p, i64]
     L.gpc_dsymv.argtypes = [C.c_int, C.c_char, i64, C.c_double, C.c_void_p, i64, C.c_void_p, C.c_double, C.c_void_p]
     L.gpc_ctx_set_profile.argtypes = [C.c_void_p, C.c_int]
     L.gpc_last_gemm_profile.argtypes = [C.c_void_p, c_double_p, C.POINTER(i64), c_double_p]

@@ -349,6 +349,55 @@ int gpc_dsymv(int device, char uplo, int64_t n, double alpha, const double* A, i
   return GPC_OK;
 }
 
+// A := alpha x x' + A on the `uplo` triangle (dsyr_, lapack.h:154-160; CMatrix::syr CMatrix.h:526-533 -- the rank-one term
+// of CGp::updateCovGradient, CGp.cpp:672-674).  HBM-bound: one pass over the triangle.
+__global__ void syr_lower_kernel(double* __restrict__ A, int64_t lda, int64_t n, double alpha, const double* __restrict__ x) {
+  const int64_t j = blockIdx.y;
+  const double axj = alpha * x[j];
+  for (int64_t i = j + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    A[i + j * lda] = fma(x[i], axj, A[i + j * lda]);
+}
+}  // extern "C"
+extern "C" int gpc_dsyr(int device, char uplo, int64_t n, double alpha, const double* x, int64_t incx, double* A, int64_t lda) {
+  if (!A || !x || n < 1 || lda < n || incx < 1 || !(is(uplo, 'U') || is(uplo, 'L'))) {
+    set_error("gpc_dsyr: bad arguments");
+    return GPC_ERR_ARG;
+  }
+  Scratch sc;
+  GPC_CHECK(sc.init(device));
+  double* dl;
+  int64_t np;
+  GPC_CHECK(stage_lower(sc, uplo, n, A, lda, &dl, &np));
+  std::vector<double> hx((size_t)n);
+  for (int64_t i = 0; i < n; i++) hx[(size_t)i] = x[i * incx];
+  double* dx;
+  GPC_CHECK(sc.alloc(&dx, (size_t)np, true));
+  GPC_CHECK(up(sc, dx, np, hx.data(), n, n, 1));
+  for (int64_t j0 = 0; j0 < n; j0 += 65535) {  // grid.y limit
+    const int64_t nj = (n - j0 < 65535) ? n - j0 : 65535;
+    dim3 grid((unsigned)((n + 1023) / 1024 < 64 ? (n + 1023) / 1024 : 64), (unsigned)nj);
+    syr_lower_kernel<<<grid, 256, 0, sc.s>>>(dl + j0 + j0 * np, np, n - j0, alpha, dx + j0);
+    GPC_CUDA_CHECK(cudaGetLastError());
+    sc.launches++;
+  }
+  // back to the caller's triangle only (the other one is not referenced by dsyr_)
+  double* dsrc = dl;
+  if (is(uplo, 'U')) {
+    double* dt;
+    GPC_CHECK(sc.alloc(&dt, (size_t)np * np, true));
+    GPC_CHECK(launch_transpose(dl, np, dt, np, n, n, sc.s, &sc.launches));
+    dsrc = dt;
+  }
+  std::vector<double> h((size_t)n * n);
+  GPC_CHECK(down(sc, h.data(), n, dsrc, np, n, n));
+  for (int64_t j = 0; j < n; j++) {
+    const int64_t lo = is(uplo, 'U') ? 0 : j, hi = is(uplo, 'U') ? j + 1 : n;
+    for (int64_t i = lo; i < hi; i++) A[i + j * lda] = h[(size_t)(i + j * n)];
+  }
+  return GPC_OK;
+}
+extern "C" {
+
 // ------------------------------------------------------------------------------------------------------
 // measurement helpers
 // ------------------------------------------------------------------------------------------------------

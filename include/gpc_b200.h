@@ -174,6 +174,8 @@ int gpc_dsyrk(int device, char uplo, char trans, int64_t n, int64_t k, double al
 /* dgemm_ (lapack.h:186-194; CMatrix::gemm CMatrix.cpp:205-247) */
 int gpc_dgemm(int device, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
               int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+/* dsyr_ (lapack.h:154-160; CMatrix::syr CMatrix.h:526-533): A := alpha x x' + A on the `uplo` triangle */
+int gpc_dsyr(int device, char uplo, int64_t n, double alpha, const double* x, int64_t incx, double* A, int64_t lda);
 /* dsymv_ (lapack.h:152-160; CMatrix::symv CMatrix.cpp:127-203) */
 int gpc_dsymv(int device, char uplo, int64_t n, double alpha, const double* A, int64_t lda, const double* x,
               double beta, double* y);

@@ -82,7 +82,7 @@ if [ -f "$SHIMDIR/libgpc_b200.so" ] && [ -d "$CPPDIR" ]; then
   mkdir -p "$OUT/obj_l2"
   CXXL="-std=gnu++98 -O3 -fPIC -w -D_LINUX -include $OUT/obj/blasmap.h -I$REF -I$HERE/../include -I$CPPDIR"
   pids=()
-  for f in GpcKernBridge CGpB200 CGplvmB200; do
+  for f in GpcKernBridge CGpB200 CGplvmB200 CCmpndKernB200; do
     g++ $CXXL -c "$CPPDIR/$f.cpp" -o "$OUT/obj_l2/$f.o" &
     pids+=($!)
   done
@@ -90,20 +90,36 @@ if [ -f "$SHIMDIR/libgpc_b200.so" ] && [ -d "$CPPDIR" ]; then
   pids+=($!)
   g++ $CXXL -include "$CPPDIR/gplvm_dropin.h" -c "$REF/gplvm.cpp" -o "$OUT/obj_l2/gplvm.o" &
   pids+=($!)
+  g++ $CXXL -include "$CPPDIR/ivm_dropin.h" -c "$REF/ivm.cpp" -o "$OUT/obj_l2/ivm.o" &
+  pids+=($!)
   g++ $CXXL -c "$HERE/../tests/cpp/cgp_b200_check.cpp" -o "$OUT/obj_l2/cgp_b200_check.o" &
   pids+=($!)
   for p in "${pids[@]}"; do wait "$p"; done
   cd "$OUT/obj"
-  L2="../obj_l2/GpcKernBridge.o ../obj_l2/CGpB200.o ../obj_l2/CGplvmB200.o"
+  L2="../obj_l2/GpcKernBridge.o ../obj_l2/CGpB200.o ../obj_l2/CGplvmB200.o ../obj_l2/CCmpndKernB200.o"
   LNK="-L$SHIMDIR -lgpc_b200 $OB -Wl,-rpath,$SP -Wl,-rpath,\$ORIGIN/../../gpc_b200 -lm"
   g++ -o "$OUT/gp_l2" ../obj_l2/gp.o $L2 CGp.o CGplvm.o $COMMON $LNK
   g++ -o "$OUT/gplvm_l2" ../obj_l2/gplvm.o $L2 CGp.o CGplvm.o $COMMON $LNK
   g++ -o "$OUT/cgp_b200_check" ../obj_l2/cgp_b200_check.o $L2 CGp.o CGplvm.o $COMMON $LNK
+  # the reference's ivm.cpp on CCmpndKernB200 (its kernel matrices K(X, X2) built on the device; `-include ivm_dropin.h`)
+  g++ -o "$OUT/ivm_l2" ../obj_l2/ivm.o $L2 CIvm.o CGp.o CGplvm.o $COMMON $LNK
+  # ---- level 1: the six CMatrix methods that wrap the hot lapack.h calls re-bound as a compiled object.
+  # The reference's own CMatrix.o keeps every other method; its six definitions are weakened (objcopy, no source change)
+  # so that the strong ones of gpc_b200/cpp/CMatrix_b200.cpp win at link time.
+  mkdir -p "$OUT/obj_l1"
+  objcopy --weaken-symbol=_ZN7CMatrix5potrfEPKc --weaken-symbol=_ZN7CMatrix5potriEPKc \
+          --weaken-symbol=_ZN7CMatrix4trsmERKS_dPKcS3_S3_S3_ --weaken-symbol=_ZN7CMatrix4syrkERKS_ddPKcS3_ \
+          --weaken-symbol=_ZN7CMatrix4gemmERKS_S1_ddPKcS3_ --weaken-symbol=_ZN7CMatrix4symvERKS_S1_ddPKc \
+          CMatrix.o "$OUT/obj_l1/CMatrix_weak.o"
+  g++ $CXXL -c "$CPPDIR/CMatrix_b200.cpp" -o "$OUT/obj_l1/CMatrix_b200.o"
+  COMMON_L1="CClctrl.o ../obj_l1/CMatrix_b200.o ../obj_l1/CMatrix_weak.o ndlfortran.o lbfgs_stub.o CNoise.o ndlutil.o ndlstrutil.o CTransform.o COptimisable.o CKern.o CDist.o ndlassert.o"
+  g++ -o "$OUT/gp_l1" gp.o CGp.o $COMMON_L1 $LNK
+  g++ -o "$OUT/ivm_l1" ivm.o CIvm.o $COMMON_L1 $LNK
   # a host test double of libgpc_b200.so made of the reference's own classes (tests/cpp/mock_gpc_b200.cpp): lets the CPU
   # tests drive the DEVICE-path logic of the C++ host classes without a GPU (LD_LIBRARY_PATH=oracle/_ref/mock)
   mkdir -p "$OUT/mock"
   g++ $CXXL -c "$HERE/../tests/cpp/mock_gpc_b200.cpp" -o "$OUT/obj_l2/mock_gpc_b200.o"
   g++ -shared -o "$OUT/mock/libgpc_b200.so" "$OUT/obj_l2/mock_gpc_b200.o" $COMMON "$OB" -Wl,-rpath,"$SP" -lm
-  echo "build_ref: built $OUT/gp_l2, gplvm_l2, cgp_b200_check (reference front-ends on CGpB200 / CGplvmB200)"
+  echo "build_ref: built $OUT/gp_l2, gplvm_l2, ivm_l2, cgp_b200_check (reference front-ends on CGpB200 / CGplvmB200 / CCmpndKernB200), gp_l1, ivm_l1 (CMatrix level 1)"
 fi
 echo "build_ref: built $OUT/libgpcref.so, gp, gplvm (OpenBLAS: $OB)"

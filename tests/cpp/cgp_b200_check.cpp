@@ -25,6 +25,7 @@
 #include <string>
 #include <vector>
 #include "CGpB200.h"
+#include "CCmpndKernB200.h"
 #include "CGplvmB200.h"
 
 static unsigned long long rngState = 88172645463325252ULL;
@@ -487,6 +488,39 @@ static int runSparseDev(unsigned int N, unsigned int D, unsigned int d, const st
   return 0;
 }
 
+// ---- the kernel-class seam: CCmpndKern (host loops, CKern.h:128-157) vs CCmpndKernB200 (gpc_kern_build / gpc_kern_cross)
+static int runKern(unsigned int N, unsigned int D, unsigned int N2, const std::string& spec)
+{
+  CMatrix X(N, D), X2(N2, D);
+  for(unsigned int j = 0; j < D; j++)
+  {
+    for(unsigned int i = 0; i < N; i++)
+      X.setVal(normal01(), i, j);
+    for(unsigned int i = 0; i < N2; i++)
+      X2.setVal(normal01(), i, j);
+  }
+  CCmpndKern ref(X);
+  CCmpndKernB200 dev(X);
+  buildKernel(ref, spec, D, false);
+  buildKernel(dev, spec, D, false);
+  CMatrix Kr(N, N), Kd(N, N), Cr(N, N2), Cd(N, N2);
+  const CKern* pr = &ref;
+  const CKern* pd = &dev; // through the base class, as CIvm / CGp::posteriorMeanVar call it
+  pr->compute(Kr, X);
+  pd->compute(Kd, X);
+  pr->compute(Cr, X, X2);
+  pd->compute(Cd, X, X2);
+  CKern* cl = dev.clone();
+  CMatrix Kc(N, N);
+  cl->compute(Kc, X);
+  printf("{\"mode\": \"kern\", \"N\": %u, \"N2\": %u, \"device_builds\": %lu, \"K_maxdiff\": %.17g, \"K2_maxdiff\": %.17g, "
+         "\"clone_maxdiff\": %.17g, \"K_symmetric\": %d, \"K_max\": %.17g}\n",
+         N, N2, dev.getNumDeviceBuilds(), Kr.maxAbsDiff(Kd), Cr.maxAbsDiff(Cd), Kr.maxAbsDiff(Kc), Kd.isSymmetric() ? 1 : 0,
+         Kr.max());
+  delete cl;
+  return 0;
+}
+
 // ---- model files: the reference as the oracle of gpc_gp_model_read / gpc_gp_model_write (tests/test_model_io_cpu.py)
 namespace
 {
@@ -734,6 +768,8 @@ int main(int argc, char** argv)
       return runDownload(N, D, d, spec);
     if(mode == "sparse") // sparse N D d seed kernels approx(1 dtc, 2 fitc, 4 dtcvar) M beta
       return runSparse(N, D, d, spec, argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 10, argc > 9 ? atof(argv[9]) : 10.0);
+    if(mode == "kern") // kern N D N2 seed kernels
+      return runKern(N, D, d, spec);
     if(mode == "sparsedev") // sparsedev N D d seed kernels approx M beta iters
       return runSparseDev(N, D, d, spec, argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 10,
                           argc > 9 ? atof(argv[9]) : 10.0, argc > 10 ? atoi(argv[10]) : 0);

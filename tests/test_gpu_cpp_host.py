@@ -203,3 +203,76 @@ def test_download_accessors_of_cgp_b200():
     assert r["rows"] == [300] * 4 and r["cols"] == [300, 300, 300, 2] and r["symmetric_flags"] == [1, 1, 0]
     assert r["err_K"] <= 1e-12 and r["err_KinvK"] <= 1e-8 and r["err_LLt"] <= 1e-10 and r["err_alpha"] <= 1e-8
     assert r["err_upper"] == 0.0
+
+
+@pytest.mark.parametrize("N,D,N2,kern", [(300, 3, 170, "rbf,lin,bias,white"), (513, 2, 64, "rbfard,matern32,matern52,poly,white"),
+                                         (100, 4, 200, "ratquad,rbf,white")])
+def test_ccmpndkern_b200_compute_matches_reference(N, D, N2, kern):
+    """The kernel-class seam of SURVEY 8(b): CKern::compute(K, X) and compute(K, X, X2) (CKern.h:128-157), called through
+    the base class as CIvm.cpp:131 / CGp.cpp:540-545 / CGplvm.cpp:348 do.  A compound with a component outside the device
+    path (ratquad) must fall through to the inherited loops, bit for bit."""
+    r = _check("kern", N, D, N2, 3, kern)
+    assert r["K_symmetric"] == 1
+    if "ratquad" in kern:
+        assert r["device_builds"] == 0 and r["K_maxdiff"] == 0.0 and r["K2_maxdiff"] == 0.0
+    else:
+        assert r["device_builds"] == 2
+        assert r["K_maxdiff"] <= 1e-12 * max(1.0, r["K_max"])       # SURVEY 8(d): K entries to 1e-12
+        assert r["K2_maxdiff"] <= 1e-12 * max(1.0, r["K_max"])
+        assert r["clone_maxdiff"] <= 1e-12 * max(1.0, r["K_max"])
+
+
+def _ivm_learn(exe, data, tmp_path):
+    out = subprocess.run([exe, "-v", "1", "-s", "1", "learn", "-a", "100", "-k", "rbf", data, str(tmp_path / "m")],
+                         cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    vals = {}
+    for key in ("Active Set Size", "rbfinverseWidth", "rbfvariance", "biasvariance", "whitevariance", "Bias on process 0"):
+        m = re.findall(re.escape(key) + r":\s*([-+0-9.eE]+)", out.stdout)
+        assert m, (key, out.stdout[-1500:])
+        vals[key] = float(m[-1])
+    return vals
+
+
+@pytest.mark.parametrize("exe", ["ivm_l2", "ivm_l1"])
+def test_reference_ivm_front_end_on_the_device_classes(tmp_path, exe):
+    """`ivm learn -a 100 -k rbf examples/unitsquaregp.svml` (README.md:234 of the reference) through (l2) the unmodified
+    ivm.cpp compiled on CCmpndKernB200 -- its kernel matrices come from the device -- and (l1) the unmodified objects with
+    the six CMatrix methods of gpc_b200/cpp/CMatrix_b200.cpp linked over the reference's weakened ones, against the plain
+    OpenBLAS build.  The IVM's point selection is discrete: 6 printed digits with a small margin."""
+    cpu, dev = os.path.join(REF, "ivm"), os.path.join(REF, exe)
+    if not (os.path.exists(cpu) and os.path.exists(dev)):
+        pytest.skip("oracle/_ref/%s not built" % exe)
+    f = np.load(os.path.join(HERE, "golden", "unitsquaregp.npz"))
+    data = str(tmp_path / "unitsquaregp.svml")
+    _write_svml(data, f["X"], np.asarray(f["y"]).ravel())
+    a, b = _ivm_learn(cpu, data, tmp_path), _ivm_learn(dev, data, tmp_path)
+    assert a["Active Set Size"] == b["Active Set Size"] == 100
+    for k in a:
+        assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+
+
+def test_reference_gp_front_end_on_level1_cmatrix(tmp_path):
+    """INTEGRATION.md level 1 as compiled code: `gp learn` with CMatrix::potrf / potri / trsm / syrk / gemm / symv bound to
+    gpc_d* (oracle/_ref/gp_l1) against the OpenBLAS build."""
+    cpu, dev = os.path.join(REF, "gp"), os.path.join(REF, "gp_l1")
+    if not (os.path.exists(cpu) and os.path.exists(dev)):
+        pytest.skip("oracle/_ref/gp_l1 not built")
+    rng = np.random.default_rng(21)
+    X = rng.standard_normal((400, 2))
+    y = np.sin(X[:, 0]) * np.cos(0.5 * X[:, 1]) + 0.1 * rng.standard_normal(400)
+    data = str(tmp_path / "data.svml")
+    _write_svml(data, X, y)
+    res = []
+    for exe in (cpu, dev):
+        out = subprocess.run([exe, "-v", "2", "learn", "-#", "8", data, str(tmp_path / "m")], cwd=str(tmp_path),
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        vals = {}
+        for key in ("rbfinverseWidth", "rbfvariance", "biasvariance", "whitevariance", "Log likelihood"):
+            m = re.findall(re.escape(key) + r":\s*([-+0-9.eE]+)", out.stdout)
+            assert m, (key, out.stdout[-1500:])
+            vals[key] = float(m[-1])
+        res.append(vals)
+    for k in res[0]:
+        assert abs(res[0][k] - res[1][k]) <= 2e-5 * max(1.0, abs(res[0][k])), (k, res)
