@@ -2,6 +2,22 @@
 #include "CCmpndKernB200.h"
 #include <cstdlib>
 
+namespace
+{
+// CComponentKern::components is protected (CKern.h:469-472): member pointer formed inside a derived class
+struct ComponentPeek : public CComponentKern
+{
+  static std::vector<CKern*> CComponentKern::*member() { return &ComponentPeek::components; }
+};
+} // namespace
+
+void CCmpndKernB200::copyComponents(const CCmpndKern& k)
+{
+  const std::vector<CKern*>& src = static_cast<const CComponentKern&>(k).*ComponentPeek::member();
+  for(size_t i = 0; i < src.size(); i++)
+    addKern(src[i]); // clones the component with its parameter values and transforms (CKern.h:382-391)
+}
+
 void CCmpndKernB200::init()
 {
   dev = 0;

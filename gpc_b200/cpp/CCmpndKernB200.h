@@ -21,8 +21,12 @@ class CCmpndKernB200 : public CCmpndKern
   CCmpndKernB200() : CCmpndKern() { init(); }
   CCmpndKernB200(unsigned int inDim) : CCmpndKern(inDim) { init(); }
   CCmpndKernB200(const CMatrix& X) : CCmpndKern(X) { init(); }
-  CCmpndKernB200(const CCmpndKern& k) : CCmpndKern(k) { init(); }
-  CCmpndKernB200(const CCmpndKernB200& k) : CCmpndKern(k) { init(); }
+  // Copies are built component by component through addKern (which clones).  The reference's own copy constructor cannot be
+  // used: CCmpndKern::CCmpndKern(const CCmpndKern&) (CKern.cpp:142-148) copies the component vector and then appends a
+  // clone of every element while iterating over the growing vector -- it never terminates (nothing in the reference
+  // copies a compound kernel, so it went unnoticed).
+  CCmpndKernB200(const CCmpndKern& k) : CCmpndKern(k.getInputDim()) { init(); copyComponents(k); }
+  CCmpndKernB200(const CCmpndKernB200& k) : CCmpndKern(k.getInputDim()) { init(); copyComponents(k); }
   virtual ~CCmpndKernB200();
   CCmpndKernB200* clone() const { return new CCmpndKernB200(*this); }
 
@@ -36,6 +40,7 @@ class CCmpndKernB200 : public CCmpndKern
  private:
   CCmpndKernB200& operator=(const CCmpndKernB200&);
   void init();
+  void copyComponents(const CCmpndKern& k);
   bool prepare(const CMatrix& X) const; // false: stay on the host path
   mutable gpc_ctx* dev;
   mutable int64_t devN;

@@ -187,6 +187,25 @@ int gpc_kern_build(gpc_ctx* c, const gpc_kcomp* comps, int ncomp)
   c->haveL = c->haveAlpha = false;
   return GPC_OK;
 }
+int gpc_kern_cross(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, const double* Xs, int64_t Ns, int64_t ldxs, double* Ks,
+                   int64_t ldk)
+{
+  CCmpndKern* kern = kernOf(comps, ncomp, c->D);
+  if(!kern || !c->haveX)
+  {
+    g_err = "mock: bad kernel specification or no X";
+    return GPC_ERR_ARG;
+  }
+  CMatrix X2(Ns, c->D);
+  for(int j = 0; j < c->D; j++)
+    for(int64_t i = 0; i < Ns; i++)
+      X2.setVal(Xs[i + j * ldxs], i, j);
+  for(int64_t j = 0; j < Ns; j++) // computeElement for every pair (CKern.h:146-157)
+    for(int64_t i = 0; i < c->N; i++)
+      Ks[i + j * ldk] = kern->computeElement(c->X, i, X2, j);
+  delete kern;
+  return GPC_OK;
+}
 int gpc_jitchol(gpc_ctx* c, int max_tries, double* jitter, double* logdet)
 {
   double added = 0.0, ld = 0.0;

@@ -199,3 +199,26 @@ def test_download_accessors_of_cgp_b200_through_the_test_double():
     assert r["rows"] == [50, 50, 50, 50] and r["cols"] == [50, 50, 50, 2] and r["symmetric_flags"] == [1, 1, 0]
     assert r["err_K"] <= 1e-12 and r["err_KinvK"] <= 1e-10 and r["err_LLt"] <= 1e-12 and r["err_alpha"] <= 1e-10
     assert r["err_upper"] == 0.0
+
+
+def test_ccmpndkern_b200_logic_through_the_test_double():
+    """CCmpndKernB200 (the CKern::compute seam): bridge flattening, context reuse, cloning (the reference's own compound
+    copy constructor never terminates, CKern.cpp:142-148 -- the class copies component by component) and the symmetric
+    flag, with the reference's loops behind gpc_kern_build / gpc_kern_cross."""
+    r = _run_mock("kern", 60, 3, 40, 3, "rbf,lin,bias,white")
+    assert r["device_builds"] == 2 and r["K_symmetric"] == 1
+    assert r["K_maxdiff"] == 0.0 and r["K2_maxdiff"] == 0.0 and r["clone_maxdiff"] == 0.0
+
+
+def test_level1_objects_resolve_the_six_cmatrix_methods():
+    """INTEGRATION.md level 1: gp_l1 / ivm_l1 are the reference's own objects with CMatrix_b200.o linked over the weakened
+    CMatrix.o -- the six hot methods must come from CMatrix_b200.cpp (they reference the gpc_d* entry points)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "gp_l1")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gp_l1 not built")
+    syms = subprocess.run(["nm", "-C", "--undefined-only", exe], capture_output=True, text=True).stdout
+    for fn in ("gpc_dpotrf", "gpc_dpotri", "gpc_dtrsm", "gpc_dsyrk", "gpc_dgemm", "gpc_dsymv"):
+        assert fn in syms, fn
+    weak = subprocess.run(["nm", "-C", os.path.join(ROOT, "oracle", "_ref", "obj_l1", "CMatrix_weak.o")], capture_output=True,
+                          text=True).stdout
+    assert " W CMatrix::potrf(char const*)" in weak and " W CMatrix::trsm(" in weak
