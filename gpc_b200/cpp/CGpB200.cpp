@@ -110,8 +110,8 @@ bool CGpB200::sameInputs() const
   const std::vector<double>& p = bridge.naturalParams();
   const CMatrix& mm = this->*memberOf(CGpMTag());
   unsigned int d = getOutputDim();
-  size_t nm = (size_t)mm.getRows() * mm.getCols();
-  if(key.size() != p.size() + 2 * d + nm)
+  size_t nm = (size_t)mm.getRows() * mm.getCols(), nx = (size_t)pX->getRows() * pX->getCols();
+  if(key.size() != p.size() + 2 * d + nm + nx)
     return false;
   for(size_t i = 0; i < p.size(); i++)
     if(key[i] != p[i])
@@ -122,6 +122,10 @@ bool CGpB200::sameInputs() const
   const double* mv = mm.getVals();
   for(size_t i = 0; i < nm; i++)
     if(key[p.size() + 2 * d + i] != mv[i])
+      return false;
+  const double* xv = pX->getVals(); // *pX changed in place without updateX() (O(N D) against O(N^3) per evaluation)
+  for(size_t i = 0; i < nx; i++)
+    if(key[p.size() + 2 * d + nm + i] != xv[i])
       return false;
   return true;
 }
@@ -134,6 +138,7 @@ void CGpB200::snapshotInputs() const
     key.push_back(getBiasVal(j));
   const CMatrix& mm = this->*memberOf(CGpMTag());
   key.insert(key.end(), mm.getVals(), mm.getVals() + (size_t)mm.getRows() * mm.getCols());
+  key.insert(key.end(), pX->getVals(), pX->getVals() + (size_t)pX->getRows() * pX->getCols());
   keyX = pX;
   keyY = py;
 }

@@ -66,9 +66,21 @@ bool CGplvmB200::onDevice() const
   return bridge.sync(pkern, pX->getCols());
 }
 
+// everything the cached evaluation was computed from: kernel parameters, the latent positions *pX and the targets m.
+// O(N (q + d)) per call against O(N^3) per evaluation; catches changes that do not go through setOptParams / updateX
+// (initXpca / initXrand after a first evaluation, pnoise->setScale / setBias / setTarget + updateSites)
+static void gplvmKey(std::vector<double>& k, const std::vector<double>& p, const CMatrix& X, const CMatrix& m)
+{
+  k = p;
+  k.insert(k.end(), X.getVals(), X.getVals() + (size_t)X.getRows() * X.getCols());
+  k.insert(k.end(), m.getVals(), m.getVals() + (size_t)m.getRows() * m.getCols());
+}
+
 void CGplvmB200::ensureEvaluated() const
 {
-  if(fresh && key == bridge.naturalParams())
+  std::vector<double> now;
+  gplvmKey(now, bridge.naturalParams(), *pX, m);
+  if(fresh && key == now)
     return;
   int64_t N = pX->getRows();
   int D = (int)pX->getCols(), d = (int)m.getCols();
@@ -104,7 +116,7 @@ void CGplvmB200::ensureEvaluated() const
     fresh = false;
     throw ndlexceptions::MatrixNonPosDef();
   }
-  key = bridge.naturalParams();
+  key.swap(now);
   fresh = true;
 }
 
