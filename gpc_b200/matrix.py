@@ -106,3 +106,13 @@ def symv(y, A, x, alpha, beta, uplo, device=0):
     x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
     check(lib().gpc_dsymv(device, _c(uplo), A.shape[0], float(alpha), ptr(A), A.shape[0], ptr(x), float(beta), ptr(y)))
     return y
+
+
+def syr(A, x, alpha, uplo, device=0):
+    """CMatrix::syr (CMatrix.h:526-533): A := alpha x x' + A on the `uplo` triangle, then mirrored (copySymmetric)."""
+    A = fmat(A).copy(order="F")
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    n = A.shape[0]
+    check(lib().gpc_dsyr(device, _c(uplo), n, float(alpha), ptr(x), 1, ptr(A), n))
+    tri = np.triu(A) if uplo.lower() == "u" else np.tril(A)
+    return tri + tri.T - np.diag(np.diag(A))

@@ -68,7 +68,7 @@ def kern_fixtures():
 
 def matrix_fixtures():
     out = {}
-    for f in ["choleskyMatrixTest", "invMatrixTest", "syrkMatrixTest", "trsmMatrixTest", "gemmMatrixTest"]:
+    for f in ["choleskyMatrixTest", "invMatrixTest", "syrkMatrixTest", "trsmMatrixTest", "gemmMatrixTest", "syrMatrixTest"]:
         m = sio.loadmat(MF + f + ".mat")
         for k, v in m.items():
             if not k.startswith("__"):

@@ -138,6 +138,33 @@ def test_trsm_matlab_fixture_all_sixteen(matrix_mat):
         assert np.abs(got - want).max() < 1e-8 * max(1.0, np.abs(want).max()), (k, mat, side, ul, tr, dg)
 
 
+def test_syr_matlab_fixture(matrix_mat):
+    """testSyr (testMatrix.cpp:1138-1203): A + alpha x x' on one triangle, mirrored -- SYR1 (x a column), SYR2 (x = row i of
+    B: stride = the leading dimension, CMatrix::syrRow CMatrix.h:535-542), SYR3 (x = column j of B), both triangles; and a
+    size across a tile edge against numpy."""
+    import ctypes as C
+    from gpc_b200._lib import check, lib, ptr
+    f = matrix_mat
+    A, B, x = f["syrMatrixTest_A"], np.asfortranarray(f["syrMatrixTest_B"]), np.ravel(f["syrMatrixTest_x"])
+    alpha = float(np.ravel(f["syrMatrixTest_alpha"])[0])
+    i, j = int(np.ravel(f["syrMatrixTest_i"])[0]) - 1, int(np.ravel(f["syrMatrixTest_j"])[0]) - 1
+    for ul in "ul":
+        assert np.abs(M.syr(A, x, alpha, ul) - f["syrMatrixTest_SYR1"]).max() < MATCHTOL
+        assert np.abs(M.syr(A, B[:, j], alpha, ul) - f["syrMatrixTest_SYR3"]).max() < MATCHTOL
+        # row i of B through the stride argument (dsyr_'s incx), as syrRow passes it
+        F = np.asfortranarray(A.copy())
+        n = F.shape[0]
+        check(lib().gpc_dsyr(0, ul.encode(), n, alpha, C.c_void_p(B.ctypes.data + 8 * i), B.shape[0], ptr(F), n))
+        tri = np.triu(F) if ul == "u" else np.tril(F)
+        assert np.abs(tri + tri.T - np.diag(np.diag(F)) - f["syrMatrixTest_SYR2"]).max() < MATCHTOL
+    rng = np.random.default_rng(2)
+    n = 300
+    S0 = rng.standard_normal((n, n))
+    S0 = S0 + S0.T
+    v = rng.standard_normal(n)
+    assert np.abs(M.syr(S0, v, -0.7, "l") - (S0 - 0.7 * np.outer(v, v))).max() < 1e-12
+
+
 def test_potrf_sizes_and_nonpd():
     rng = np.random.default_rng(3)
     for n in [1, 5, 127, 128, 129, 300, 1000, 2050]:
