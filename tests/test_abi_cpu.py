@@ -82,6 +82,30 @@ def test_compute_fails_loudly_without_gpu():
         G.CGp(G.make_kern(["rbf", "white"], 2), np.zeros((4, 2)), np.zeros((4, 1)))
 
 
+@pytest.mark.skipif(G.lib().gpc_device_count() > 0, reason="only meaningful without a GPU")
+def test_sharded_and_sparse_entry_points_fail_loudly_without_gpu():
+    L = G.lib()
+    h = C.c_void_p()
+    devs = (C.c_int * 2)(0, 0)
+    assert L.gpc_dist_create_local(C.byref(h), devs, 2, 1, 2, 1000, 3, 1, 128) < 0 and not h.value
+    assert L.gpc_dist_create_nccl(C.byref(h), 0, 0, 1, None, 1, 1, 1000, 3, 1, 128) < 0 and not h.value
+    assert L.gpc_sparse_create(C.byref(h), 0, 1, 1000, 50, 3, 1) < 0 and not h.value
+    assert len(L.gpc_last_error()) > 0
+
+
+def test_sharded_entry_points_reject_bad_shapes():
+    """argument checks that need no device: P * Q must equal the number of ranks, nb a multiple of 128"""
+    L = G.lib()
+    h = C.c_void_p()
+    devs = (C.c_int * 2)(0, 0)
+    assert L.gpc_dist_create_local(C.byref(h), devs, 2, 2, 2, 1000, 3, 1, 128) == -1      # 2 x 2 grid on 2 ranks
+    assert L.gpc_dist_create_local(C.byref(h), devs, 2, 1, 2, 1000, 3, 1, 100) == -1      # nb not a multiple of 128
+    assert L.gpc_sparse_create(C.byref(h), 0, 3, 1000, 50, 3, 1) == -1                    # PITC (3) is not offered
+    out = (C.c_int * 12)()
+    assert L.gpc_dist_plan(2, 4, 8, 1000, 128, 0, out, None) == -1                         # rank out of range
+    assert L.gpc_dist_plan(2, 4, 7, 1000, 128, 0, out, None) == 0 and out[0] == 8          # 8 block rows
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under gpc_b200/ may import or load it."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "gpc_b200")):

@@ -27,7 +27,8 @@ def _problem(N, D, d, seed=3):
 
 
 @pytest.mark.parametrize("N,nb,grid", [(300, 128, (1, 1)), (1000, 256, (1, 1)), (700, 128, (1, 2)), (1000, 128, (2, 2)),
-                                       (1500, 256, (2, 4)), (1100, 128, (2, 4)), (900, 128, (4, 2)), (640, 128, (3, 1))])
+                                       (1500, 256, (2, 4)), (1100, 128, (2, 4)), (900, 128, (4, 2)), (640, 128, (3, 1)),
+                                       (300, 128, (4, 2))])   # the last one: more process rows than block rows
 def test_one_sweep_virtual_ranks_vs_oracle(N, nb, grid):
     """all ranks of a P x Q grid as worker threads on device 0: ll, gradient and K^-1 itself against the oracle"""
     from gpc_b200.dist import DistGp
