@@ -429,8 +429,7 @@ static int sweep(DistRank& r) {
   const OzCycGrid gr{P, Q, p, q};
   const size_t sb = oz_slot_bytes(nb, r.S);
   std::vector<BcastItem> items((size_t)NBt);
-  // events: 0 slots arrived, 1 bulk done, 2 W ready, 3 W arrived, 4..7 panel chunks produced
-  auto EV = [&](int kind, int k) { return r.ev[(size_t)kind * NBt + k]; };
+  auto EV = [&](int kind, int k) { return r.ev[(size_t)kind * NBt + k]; };  // 0 slots arrived, 1 bulk done, 2 W ready, 3 W arrived, 4 panel produced
   for (int k = 0; k < NBt; k++) {
     const int b = k & 1;
     const bool col_owner = (q == k % Q), row_owner = (p == k % P), diag_owner = col_owner && row_owner;
@@ -463,51 +462,37 @@ static int sweep(DistRank& r) {
     GPC_CUDA_CHECK(cudaEventRecord(EV(3, k), r.s_comm));
     GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_panel, EV(3, k), 0));
     PROF(k, 3, r.s_panel);
-    // ---- this rank's blocks of panel k, sliced straight into their slots, and the panel to everybody: one broadcast per
-    //      slot, rooted at the rank that produced it.  The panel goes out in up to four chunks (three ranges of the block
-    //      column below the diagonal, then block row k with the diagonal block), each broadcast as soon as it is sliced, so
-    //      that the transfer of one chunk overlaps the production of the next.
-    {
-      const int below = NBt - k - 1;
-      const int ncol = below >= 12 ? 3 : (below >= 6 ? 2 : (below > 0 ? 1 : 0));
-      int chunk = 0;
-      for (int c = 0; c < ncol; c++, chunk++) {
-        const int g0 = k + 1 + (int)((int64_t)below * c / ncol), g1 = k + 1 + (int)((int64_t)below * (c + 1) / ncol);
-        if (col_owner) {  // L_ik = A_ik W_kk'  for the local block rows with global index in [g0, g1)
-          const int il0 = r.lrow_lb(g0), il1 = r.lrow_lb(g1);
-          const int64_t m = (int64_t)(il1 - il0) * nb;
-          if (m > 0) {
-            GemmCall g{r.T + (int64_t)il0 * nb + (int64_t)(k / Q) * nb * r.ML, r.Wb, r.Lp, r.ML, nb, m, m, nb, nb, 1.0, 0.0,
-                       false, false, false};
-            g.b_tri = -1;
-            GPC_CHECK(launch_gemm(g, r.s_panel, &r.launches));
-            GPC_CHECK(oz_slice_to_slots(r.Lp, m, false, m, nb, r.S, r.emax, r.slots[b], il0 * P + p, P, r.s_panel, &r.launches));
-          }
-        }
-        GPC_CUDA_CHECK(cudaEventRecord(EV(4 + chunk, k), r.s_panel));
-        GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_comm, EV(4 + chunk, k), 0));
-        int n = 0;
-        for (int g = g0; g < g1; g++) items[(size_t)n++] = BcastItem{r.slots[b] + (size_t)g * sb, sb, r.producer(g, k)};
-        GPC_CHECK(r.comm->bcast_group(items.data(), n, r.s_comm));
+    // ---- this rank's blocks of panel k, sliced straight into their slots
+    if (col_owner) {  // L_ik = A_ik W_kk'  for the local block rows with global index > k
+      const int il0 = r.lrow_lb(k + 1);
+      const int64_t m = r.ML - (int64_t)il0 * nb;
+      if (m > 0) {
+        GemmCall g{r.T + (int64_t)il0 * nb + (int64_t)(k / Q) * nb * r.ML, r.Wb, r.Lp, r.ML, nb, m, m, nb, nb, 1.0, 0.0,
+                   false, false, false};
+        g.b_tri = -1;
+        GPC_CHECK(launch_gemm(g, r.s_panel, &r.launches));
+        GPC_CHECK(oz_slice_to_slots(r.Lp, m, false, m, nb, r.S, r.emax, r.slots[b], il0 * P + p, P, r.s_panel, &r.launches));
       }
-      if (row_owner) {  // R_kj' = B_kj' W_kk'  for the local block columns with global index < k
-        const int64_t m = (int64_t)r.lcol_lb(k) * nb;
-        if (m > 0) {
-          GemmCall g{r.T + (int64_t)(k / P) * nb, r.Wb, r.Lp, r.ML, nb, m, m, nb, nb, 1.0, 0.0, true, false, false};
-          g.b_tri = -1;
-          GPC_CHECK(launch_gemm(g, r.s_panel, &r.launches));
-          GPC_CHECK(oz_slice_to_slots(r.Lp, m, false, m, nb, r.S, r.emax, r.slots[b], q, Q, r.s_panel, &r.launches));
-        }
-      }
-      if (diag_owner)  // S_k = W_kk'
-        GPC_CHECK(oz_slice_to_slots(r.Wb, nb, true, nb, nb, r.S, r.emax, r.slots[b], k, 0, r.s_panel, &r.launches));
-      PROF(k, 4, r.s_panel);
-      GPC_CUDA_CHECK(cudaEventRecord(EV(4 + chunk, k), r.s_panel));
-      GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_comm, EV(4 + chunk, k), 0));
-      int n = 0;
-      for (int g = 0; g <= k; g++) items[(size_t)n++] = BcastItem{r.slots[b] + (size_t)g * sb, sb, r.producer(g, k)};
-      GPC_CHECK(r.comm->bcast_group(items.data(), n, r.s_comm));
     }
+    if (row_owner) {  // R_kj' = B_kj' W_kk'  for the local block columns with global index < k
+      const int64_t m = (int64_t)r.lcol_lb(k) * nb;
+      if (m > 0) {
+        GemmCall g{r.T + (int64_t)(k / P) * nb, r.Wb, r.Lp, r.ML, nb, m, m, nb, nb, 1.0, 0.0, true, false, false};
+        g.b_tri = -1;
+        GPC_CHECK(launch_gemm(g, r.s_panel, &r.launches));
+        GPC_CHECK(oz_slice_to_slots(r.Lp, m, false, m, nb, r.S, r.emax, r.slots[b], q, Q, r.s_panel, &r.launches));
+      }
+    }
+    if (diag_owner)  // S_k = W_kk'
+      GPC_CHECK(oz_slice_to_slots(r.Wb, nb, true, nb, nb, r.S, r.emax, r.slots[b], k, 0, r.s_panel, &r.launches));
+    PROF(k, 4, r.s_panel);
+    GPC_CUDA_CHECK(cudaEventRecord(EV(4, k), r.s_panel));
+    // ---- the panel to everybody: one broadcast per slot, from the rank that produced it, all in ONE group.  (Sending it
+    //      in chunks as they are sliced, so that transfer overlaps production, was measured on 8 GPUs and is slower: every
+    //      additional NCCL group costs more launch latency than the overlap returns -- C3 0.092 -> 0.102 s.)
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(r.s_comm, EV(4, k), 0));
+    for (int g = 0; g < NBt; g++) items[(size_t)g] = BcastItem{r.slots[b] + (size_t)g * sb, sb, r.producer(g, k)};
+    GPC_CHECK(r.comm->bcast_group(items.data(), NBt, r.s_comm));
     PROF(k, 5, r.s_comm);
     GPC_CUDA_CHECK(cudaEventRecord(EV(0, k), r.s_comm));
     // ---- bulk update of step k: every local block except block row / column k+1 (done by the look-ahead of step k+1)
