@@ -595,6 +595,11 @@ def main():
                         if gold:
                             r_["parity_vs_reference"] = parity(r_["ll"], r_["g"], gold)
                     barrier()
+                    if imma.value > 0:   # absolute rate and fraction of the measured int8-pipe roofline, per GPU
+                        pk_ = imma.value / (S * (S + 1) / 2.0)
+                        r_["tflops_equiv_per_gpu"] = r_["tflops_equiv"] / world
+                        r_["roofline_frac_per_gpu"] = r_["tflops_equiv"] / world / pk_
+                        r_["roofline_peak_per_gpu"] = pk_
                     sharded[wl] = r_
                 except Exception as e:
                     sharded[wl] = {"error": str(e)}
