@@ -99,6 +99,24 @@ __device__ __forceinline__ void oz_tc_fence_after() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void oz_tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// int32 -> fp64 without I2F.F64 (a quarter-rate conversion on the fp64 pipe; the epilogue converts 512 values per
+// thread): 2^52 + (x + 2^31) is built exactly from the bits, one full-rate DADD removes the offset
+__device__ __forceinline__ double oz_i2d(int x) {
+  return __hiloint2double(0x43300000, (int)((unsigned)x ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+}
+// two TMEM loads in flight behind ONE wait (halves the exposed TMEM round trips of the epilogue)
+__device__ __forceinline__ void oz_tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, int (&r0)[16], int (&r1)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]),
+        "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15]), "=r"(r1[0]),
+        "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]), "=r"(r1[9]),
+        "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+      : "r"(taddr0), "r"(taddr1)
+      : "memory");
+}
 __device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, int (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -519,16 +537,29 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 #pragma unroll
     for (int ch = 0; ch < OZ_BN / 16; ch++) {
       double acc[16];
-      int r[16];
+      int r[16], r2[16];
       double* cp = crow + (int64_t)(ch * 16) * a.ldc;
-      oz_tmem_ld16(trow + (uint32_t)((S - 1) * OZ_BN + ch * 16), r);
-#pragma unroll
-      for (int j = 0; j < 16; j++) acc[j] = (double)r[j];
-#pragma unroll
-      for (int l = S - 2; l >= 0; l--) {
+      // Horner over the levels, most significant last: two levels per TMEM round trip
+      int l = S - 1;
+      if (S & 1) {
         oz_tmem_ld16(trow + (uint32_t)(l * OZ_BN + ch * 16), r);
 #pragma unroll
-        for (int j = 0; j < 16; j++) acc[j] = fma(acc[j], 0.00390625, (double)r[j]);  // 2^-8 per level
+        for (int j = 0; j < 16; j++) acc[j] = oz_i2d(r[j]);
+        l--;
+      } else {
+        oz_tmem_ld16x2(trow + (uint32_t)(l * OZ_BN + ch * 16), trow + (uint32_t)((l - 1) * OZ_BN + ch * 16), r, r2);
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] = fma(oz_i2d(r[j]), 0.00390625, oz_i2d(r2[j]));
+        l -= 2;
+      }
+#pragma unroll
+      for (; l >= 1; l -= 2) {
+        oz_tmem_ld16x2(trow + (uint32_t)(l * OZ_BN + ch * 16), trow + (uint32_t)((l - 1) * OZ_BN + ch * 16), r, r2);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          acc[j] = fma(acc[j], 0.00390625, oz_i2d(r[j]));   // 2^-8 per level
+          acc[j] = fma(acc[j], 0.00390625, oz_i2d(r2[j]));
+        }
       }
 #pragma unroll
       for (int j = 0; j < 16; j++) {
