@@ -76,6 +76,7 @@ bool oz_wants(const GemmCall& g);
 int oz_slices();                  // configured number of slices  // true when launch_gemm should route this call to launch_gemm_ozaki
 int launch_gemm_ozaki(const GemmCall& g, cudaStream_t s, int64_t* launches, int slices = 0);  // 0: configured
 void oz_release_device(int dev);   // frees the per-device slice workspace
+void oz_set_debug(long long* dev_stamps, int cta);  // clock64 phase stamps of one CTA of the next GEMM launches (null: off)
 // ---- block-cyclic one-sweep mode (dist.cu): panels pre-sliced into "slots", staircase update of the local matrix ----
 struct OzCycMaps {   // the two tensor maps (A: 128-row boxes, B: 64-row boxes) over one slot buffer
   alignas(64) unsigned char opaque[2 * 128 + 128];

@@ -492,6 +492,32 @@ int gpc_set_gemm_engine(int ozaki, int slices, int64_t min_mn, int64_t min_k) {
 
 int gpc_gemm_engine_slices(void) { return oz_slices(); }
 
+// clock64 phase stamps (8 entries, relative to the CTA's start) of CTA `cta` of one tensor-core GEMM m x n x k:
+// [0] start [1] barriers + TMEM ready [2] first operands landed [3] last MMA issued [4] C segment requested
+// [5] accumulators complete [6] epilogue stores issued [7] end
+int gpc_bench_oz_stamps(int device, int64_t m, int64_t n, int64_t k, int cta, long long* stamps8) {
+  if (m % TILE || n % TILE || k % TILE || !stamps8) return GPC_ERR_ARG;
+  Scratch sc;
+  GPC_CHECK(sc.init(device));
+  double *A, *B, *Cm;
+  long long* st;
+  GPC_CHECK(sc.alloc(&A, (size_t)m * k, true));
+  GPC_CHECK(sc.alloc(&B, (size_t)n * k, true));
+  GPC_CHECK(sc.alloc(&Cm, (size_t)m * n, true));
+  GPC_CHECK(sc.alloc((double**)&st, 16, true));
+  GemmCall g{A, B, Cm, m, n, m, m, n, k, -1.0, 1.0, false, false, false};
+  GPC_CHECK(launch_gemm_ozaki(g, sc.s, &sc.launches));  // warm-up (workspaces, attributes)
+  oz_set_debug(st, cta);
+  int rc = launch_gemm_ozaki(g, sc.s, &sc.launches);
+  oz_set_debug(nullptr, 0);
+  if (rc != GPC_OK) return rc;
+  long long h[8];
+  GPC_CUDA_CHECK(cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, sc.s));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(sc.s));
+  for (int i = 0; i < 8; i++) stamps8[i] = h[i] - h[0];
+  return GPC_OK;
+}
+
 int gpc_bench_leaf(int device, int reps, double* us_out, long long* stamps_out) {
   // the 128 x 128 diagonal-block kernel on a well-conditioned SPD block, timed in isolation; stamps_out (32 entries)
   // receives the clock64 phase stamps of the last launch relative to its start

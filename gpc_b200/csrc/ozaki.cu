@@ -301,6 +301,8 @@ struct OzArgs {
   int bm0, bn0;          // tile offsets of the launched sub-rectangle inside the local matrix
   int slot_rows;         // rows (of nb bytes) per slot = S * nb + 8
   const uint8_t* slots;  // base of the slot buffer (for the row scales)
+  long long* dbg;        // non-null: clock64 phase stamps of CTA dbg_cta (tools/oz_stamps.py), 8 entries
+  int dbg_cta;
 };
 
 __device__ __forceinline__ uint32_t oz_elect_one() {
@@ -370,6 +372,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     bm = first + rem % gsz;
     bn = rem / gsz;
   }
+  const bool dbg_on = a.dbg != nullptr && (int)blockIdx.x == a.dbg_cta;
+  if (dbg_on && threadIdx.x == 0) a.dbg[0] = clock64();  // 0: CTA start
   if (a.lower && bn > 2 * bm + 1) return;  // whole CTA, before any barrier / TMEM allocation
   // operand row coordinates of slice 0 in the tensor maps, slice-to-slice stride, scales, and the per-tile alpha / beta
   int a_row0, b_row0, a_ss = a.RpadA, b_ss = a.RpadB;
@@ -458,6 +462,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   __syncthreads();
   oz_tc_fence_after();
   const uint32_t tmem = *s_tmem;
+  if (dbg_on && threadIdx.x == 0) a.dbg[1] = clock64();  // 1: barriers initialised, TMEM allocated
 
   if (warp == 4) {
     if (lane == 0) {
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     for (int kb = kb0; kb < KB; kb++) {
       const int it = kb - kb0, set = it & 1;
       oz_mbar_wait(FULL_B(set), (it >> 1) & 1, a.errflag, 3);
+      if (dbg_on && lane == 0 && it == 0) a.dbg[2] = clock64();  // 2: first operands have landed
       const uint32_t b_lo = b_lo0 + (uint32_t)set * (S * OZ_B_BYTES >> 4);
       const uint32_t first_acc = it == 0 ? 0u : 1u;
 #define OZ_SLICE(P)                                                            \
@@ -513,6 +519,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     }
     if (oz_elect_one()) oz_tc_commit(TMEM_FULL);
     __syncwarp();
+    if (dbg_on && lane == 0) a.dbg[3] = clock64();  // 3: last MMA issued
   } else {
     // ===== epilogue warps 0..3: TMEM lane = output row =====
     if (tid < OZ_BN) s_cscale[tid] = scaleB[tid];
@@ -532,8 +539,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 #pragma unroll
       for (int j = 0; j < OZ_BN; j++) cv[j] = 0.0;
     }
+    if (dbg_on && tid == 0) a.dbg[4] = clock64();  // 4: C row segment requested
     while (!oz_mbar_try_wait(TMEM_FULL, 0)) __nanosleep(256);  // stay out of the issuer's way while the tile is computed
     oz_tc_fence_after();
+    if (dbg_on && tid == 0) a.dbg[5] = clock64();  // 5: accumulators complete
 #pragma unroll
     for (int ch = 0; ch < OZ_BN / 16; ch++) {
       double acc[16];
@@ -568,12 +577,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       }
     }
   }
+  if (dbg_on && tid == 0) a.dbg[6] = clock64();  // 6: epilogue stores issued (thread 0)
   oz_tc_fence_before();
   __syncthreads();
   if (warp == 5) {
     oz_tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
+  if (dbg_on && tid == 0) a.dbg[7] = clock64();  // 7: end
+}
+
+static long long* g_oz_dbg = nullptr;
+static int g_oz_dbg_cta = 0;
+void oz_set_debug(long long* dev_stamps, int cta) {
+  g_oz_dbg = dev_stamps;
+  g_oz_dbg_cta = cta;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -820,6 +838,8 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   a.RpadA = (int)c.m;
   a.RpadB = (int)c.n;
   a.errflag = w.errflag;
+  a.dbg = g_oz_dbg;
+  a.dbg_cta = g_oz_dbg_cta;
   const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
   // k chunks: per unit of k a level sums <= 8 products, two of them with a first digit (|d_0| <= 65), the others with
   // |d| <= 128: (6 * 2^14 + 2 * 65 * 128) * k < 2^31  ->  k <= 18683: chunks of 128 k-blocks (16384)

@@ -258,6 +258,10 @@ int gpc_bench_syrk(int device, int64_t n, int64_t k, int reps, double* ms);
 /* the 128 x 128 diagonal-block kernel (Cholesky + inverse of the factor, N/128 times on the critical path) in
  * isolation: *us per launch; stamps (32 entries) = clock64 phase stamps of one launch relative to its start */
 int gpc_bench_leaf(int device, int reps, double* us, long long* stamps);
+/* clock64 phase stamps (8 entries, relative to the CTA's start) of CTA `cta` of one tensor-core GEMM m x n x k (kernel tuning):
+ * start, barriers + TMEM ready, first operands landed, last MMA issued, C segment requested, accumulators complete,
+ * epilogue stores issued, end */
+int gpc_bench_oz_stamps(int device, int64_t m, int64_t n, int64_t k, int cta, long long* stamps8);
 /* one GEMM shape on device scratch with a forced tile configuration (cfg 0..3, -1 = heuristic): kernel tuning */
 int gpc_bench_gemm(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, int reps,
                    double* ms);
