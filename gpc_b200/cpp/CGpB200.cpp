@@ -232,7 +232,8 @@ bool CGpB200::sameSparseInputs() const
   const CMatrix& mm = this->*memberOf(CGpMTag());
   unsigned int d = getOutputDim();
   size_t nm = (size_t)mm.getRows() * mm.getCols(), nu = (size_t)X_u.getRows() * X_u.getCols();
-  if(skey.size() != p.size() + 2 * d + 1 + nu + nm)
+  size_t nx = (size_t)pX->getRows() * pX->getCols();
+  if(skey.size() != p.size() + 2 * d + 1 + nu + nm + nx)
     return false;
   size_t c = 0;
   for(size_t i = 0; i < p.size(); i++)
@@ -253,6 +254,10 @@ bool CGpB200::sameSparseInputs() const
   const double* mv = mm.getVals();
   for(size_t i = 0; i < nm; i++)
     if(skey[c++] != mv[i])
+      return false;
+  const double* xv = pX->getVals();
+  for(size_t i = 0; i < nx; i++)
+    if(skey[c++] != xv[i])
       return false;
   return true;
 }
@@ -301,6 +306,7 @@ void CGpB200::ensureSparseEvaluated() const
   skey.push_back(getBetaVal());
   skey.insert(skey.end(), X_u.getVals(), X_u.getVals() + (size_t)X_u.getRows() * X_u.getCols());
   skey.insert(skey.end(), mm.getVals(), mm.getVals() + (size_t)mm.getRows() * mm.getCols());
+  skey.insert(skey.end(), pX->getVals(), pX->getVals() + (size_t)pX->getRows() * pX->getCols());
   keyX = pX;
   keyY = py;
   sstate = EVALUATED;
