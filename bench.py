@@ -210,8 +210,21 @@ def sharded_headline(args, G, name, kern, tp0, X, y, rank, world, local_rank):
     except Exception:
         pass
     bf16 = float(mp.get("bf16_tflops", 1590.0))
-    S = 8
+    from gpc_b200._lib import check, lib
+    S = int(lib().gpc_gemm_engine_slices())
     pk = 2.0 * bf16 / (S * (S + 1) / 2.0)
+    pk_src = "fp64-equivalent of 2 x bf16_tflops / 36, per GPU (int8 peak measurement failed)"
+    pks = None
+    try:   # the int8 pipe measured on this GPU: burst, and sustained over 2 s (the step is long: the power cap applies)
+        b_, s_ = C.c_double(0), C.c_double(0)
+        check(lib().gpc_bench_imma_peak(local_rank, 4, C.byref(b_)))
+        check(lib().gpc_bench_imma_peak_sustained(local_rank, 4, 2.0, C.byref(s_)))
+        pk = b_.value / (S * (S + 1) / 2.0)
+        pks = s_.value / (S * (S + 1) / 2.0)
+        pk_src = ("fp64-equivalent of the int8 tensor pipe measured on this GPU (gpc_bench_imma_peak, burst %.0f TOP/s; "
+                  "sustained over 2 s %.0f TOP/s) / %d, per GPU" % (b_.value, s_.value, S * (S + 1) // 2))
+    except Exception:
+        pass
     sweep_ms = info["phases_ms"]["sweep"]
     ach = float(N) ** 3 / world / (sweep_ms * 1e-3) / 1e12
     line = {
@@ -227,7 +240,7 @@ def sharded_headline(args, G, name, kern, tp0, X, y, rank, world, local_rank):
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "oz_gemm_kernel in block-cyclic mode (bulk rank-nb update of the local matrix)",
                      "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
-                     "peak_source": "fp64-equivalent of the int8 tensor pipe, 2 x bf16_tflops / 36, per GPU",
+                     "peak_source": pk_src, "sustained_peak": pks, "frac_of_sustained_peak": (ach / pks) if pks else None,
                      "note": "achieved = N^3 / ranks / sweep time of rank 0 (panel production and broadcasts included)"},
         "cpu_baseline": None, "ll": ll, "tflops_equiv_total": float(N) ** 3 / (ms_dev / args.steps * 1e-3) / 1e12,
         "sharded": {"comm_nranks": info["ranks"], "per_rank_matrix_bytes": info["local_matrix_bytes"],
@@ -490,6 +503,7 @@ def main():
     peak = C.c_double(0)
     check(lib().gpc_bench_dmma_peak(local_rank, C.byref(peak)))
     imma = C.c_double(0)   # measured INT8 tensor-pipe peak of this GPU (tcgen05.mma.kind::i8, TMEM/SMEM-resident loop), TOP/s
+    imma_sus = C.c_double(0)   # the same loop kept running for 2 s: the rate under the clock the power cap leaves
     try:
         check(lib().gpc_bench_imma_peak(local_rank, 4, C.byref(imma)))
     except Exception:
@@ -534,6 +548,8 @@ def main():
                             "per fp64 MMA" % (imma.value, S * (S + 1) // 2)) if imma.value > 0 else
                            "fp64-equivalent of 2 x %s (imma peak measurement failed)" % bf16_src,
             "int8_peak_tops_measured": imma.value,
+            "peak_note": "burst figure (pseudo-random operands): the C2 step is 13 ms of mixed kernels; the long C3 / C4 legs "
+                         "are also given against the sustained figure (2 s of the same loop under the power cap)",
             "peak_from_2x_bf16": pk_bf16, "frac_of_2x_bf16_peak": ach / pk_bf16,
             "int8_mmas_per_fp64_mma": S * (S + 1) // 2,
             "launches_per_eval": oz_n, "kernel_ms_per_eval": oz_ms, "algorithmic_flops": oz_fl,
@@ -572,6 +588,9 @@ def main():
                 also["c4"] = sharded_leg(G, "c4", local_rank, 1, None, nb=2048, reps=2)
             except Exception as e:
                 also["c4"] = {"error": str(e)}
+            for leg in also.values():
+                if "tflops_equiv" in leg and imma.value > 0:
+                    leg["roofline_frac"] = leg["tflops_equiv"] / (imma.value / (S * (S + 1) / 2.0))
         if world > 1:
             # the path that SHARDS: K -> K^-1 2-D block-cyclic over all ranks, NCCL panel broadcasts;
             # C3 (strong scaling against this run's own single-GPU evaluation on rank 0) and C4 (BASELINE configs[3])
@@ -603,6 +622,25 @@ def main():
                     sharded[wl] = r_
                 except Exception as e:
                     sharded[wl] = {"error": str(e)}
+
+    # ---- the SUSTAINED int8-pipe rate (2 s of the same MMA loop on pseudo-random operands: the clock the 1000 W power cap
+    #      leaves), measured last so that it does not heat the GPU before the timed legs: the denominator for the long steps
+    if rank == 0 and imma.value > 0:
+        try:
+            check(lib().gpc_bench_imma_peak_sustained(local_rank, 4, 2.0, C.byref(imma_sus)))
+        except Exception:
+            imma_sus = C.c_double(0)
+        if imma_sus.value > 0:
+            pks_ = imma_sus.value / (S * (S + 1) / 2.0)
+            roofline["int8_peak_tops_sustained_2s"] = imma_sus.value
+            roofline["frac_of_sustained_peak"] = roofline["achieved"] / pks_ if roofline.get("bound") == "tensor" and "int8_mmas_per_fp64_mma" in roofline else None
+            for leg in (also or {}).values():
+                if isinstance(leg, dict) and "tflops_equiv" in leg:
+                    leg["roofline_frac_sustained_peak"] = leg["tflops_equiv"] / pks_
+            for leg in (sharded or {}).values():
+                if isinstance(leg, dict) and "tflops_equiv" in leg:
+                    leg["roofline_frac_per_gpu_sustained_peak"] = leg["tflops_equiv"] / world / pks_
+                    leg["roofline_sustained_peak_per_gpu"] = pks_
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1009,7 +1009,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_imma_peak_kernel(int iters, 
   uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + OZ_A_BYTES + 4 * OZ_B_BYTES);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + OZ_A_BYTES + 4 * OZ_B_BYTES + 64);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < (OZ_A_BYTES + 4 * OZ_B_BYTES) / 4; i += OZ_THREADS) reinterpret_cast<uint32_t*>(gbase)[i] = 0x01010101u;
+  // pseudo-random operand bytes: switching activity (and therefore power and the clock the power cap allows) like real slices
+  for (int i = tid; i < (OZ_A_BYTES + 4 * OZ_B_BYTES) / 4; i += OZ_THREADS) {
+    uint32_t x = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    x ^= x >> 15;
+    x *= 2246822519u;
+    x ^= x >> 13;
+    reinterpret_cast<uint32_t*>(gbase)[i] = x;
+  }
   const uint32_t bar0 = smem_u32(bars);
   if (warp == 4 && lane == 0) {
     oz_mbar_init(bar0, 1);
@@ -1058,6 +1065,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_imma_peak_kernel(int iters, 
   }
 }
 
+int oz_bench_imma_peak_sustained(int device, int nwide, double seconds, double* tops);
 int oz_bench_imma_peak(int device, int nwide, double* tops) {
   GPC_CUDA_CHECK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -1100,6 +1108,49 @@ int oz_bench_imma_peak(int device, int nwide, double* tops) {
   return GPC_OK;
 }
 
+int oz_bench_imma_peak_sustained(int device, int nwide, double seconds, double* tops) {
+  GPC_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GPC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (nwide < 1 || nwide > 4) nwide = 4;
+  if (!(seconds > 0.05)) seconds = 0.05;
+  if (seconds > 20.0) seconds = 20.0;
+  const size_t smem = 1024 + OZ_A_BYTES + 4 * OZ_B_BYTES + 256;
+  GPC_CUDA_CHECK(cudaFuncSetAttribute(oz_imma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int* err = nullptr;
+  GPC_CUDA_CHECK(cudaMalloc(&err, sizeof(int)));
+  GPC_CUDA_CHECK(cudaMemset(err, 0, sizeof(int)));
+  cudaStream_t s;
+  GPC_CUDA_CHECK(cudaStreamCreate(&s));
+  const int ctas = prop.multiProcessorCount, iters = 4096;
+  const double ops = (double)ctas * iters * 8.0 * (OZ_BK / OZ_UK) * 2.0 * OZ_BM * (double)(nwide * OZ_BN) * OZ_UK;
+  const int launches = (int)(seconds / (ops / 4.0e15)) + 4;  // ~9 ms each at the burst rate
+  const int half = launches / 2;
+  cudaEvent_t e0, e1;
+  GPC_CUDA_CHECK(cudaEventCreate(&e0));
+  GPC_CUDA_CHECK(cudaEventCreate(&e1));
+  for (int i = 0; i < launches; i++) {
+    if (i == half) GPC_CUDA_CHECK(cudaEventRecord(e0, s));
+    oz_imma_peak_kernel<<<ctas, OZ_THREADS, smem, s>>>(iters, nwide, err);
+  }
+  GPC_CUDA_CHECK(cudaEventRecord(e1, s));
+  GPC_CUDA_CHECK(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  int herr = 0;
+  cudaMemcpy(&herr, err, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(err);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(s);
+  if (herr) {
+    set_error("oz_bench_imma_peak_sustained: pipeline protocol error");
+    return GPC_ERR_CUDA;
+  }
+  if (tops) *tops = ops * (launches - half) / (ms * 1e-3) / 1e12;
+  return GPC_OK;
+}
+
 void oz_release_device(int dev) {
   if (dev < 0 || dev >= 64) return;
   std::lock_guard<std::mutex> lk(g_oz_mu);
@@ -1131,6 +1182,11 @@ void oz_release_device(int dev) {
 
 // measured INT8 tensor-pipe peak of this device in TOP/s (ops = 2 x MACs); nwide = N / 64 of the instruction (1..4)
 extern "C" int gpc_bench_imma_peak(int device, int nwide, double* tops) { return gpc::oz_bench_imma_peak(device, nwide, tops); }
+// the same loop kept running for `seconds` (back-to-back launches): the SUSTAINED rate over the second half, i.e. under
+// whatever clock the power cap leaves (the roofline of a kernel timed inside a long step); *mhz_hint is not measured here
+extern "C" int gpc_bench_imma_peak_sustained(int device, int nwide, double seconds, double* tops) {
+  return gpc::oz_bench_imma_peak_sustained(device, nwide, seconds, tops);
+}
 
 extern "C" int gpc_oz_slice_check(int device, int64_t R, int64_t K, int kc, int S, const double* X, signed char* slices_out,
                                   double* scale_out) {

@@ -253,6 +253,9 @@ int gpc_bench_dmma_peak(int device, double* tflops);
  * M = 128, N = 64 nwide (nwide 1..4), K = 32 on shared-memory-resident operands into TMEM; *tops = 2 x MACs / s / 1e12.
  * The fp64-equivalent peak of the engine is tops / (S (S + 1) / 2) for S slices (36 int8 MMAs per fp64 MMA at S = 8). */
 int gpc_bench_imma_peak(int device, int nwide, double* tops);
+/* the same loop kept running for `seconds`: the SUSTAINED rate over the second half (under the clock the power cap leaves) --
+ * the denominator for a kernel timed inside a long step, where the burst figure above is not reachable */
+int gpc_bench_imma_peak_sustained(int device, int nwide, double seconds, double* tops);
 /* C(n x n) -= A(n x k) A' (lower) on device scratch: the SYRK trailing update in isolation.  *ms per launch */
 int gpc_bench_syrk(int device, int64_t n, int64_t k, int reps, double* ms);
 /* the 128 x 128 diagonal-block kernel (Cholesky + inverse of the factor, N/128 times on the critical path) in
