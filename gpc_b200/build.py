@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpc_b200.so")
 SHIM = os.path.join(HERE, "libgpc_lapack_shim.so")
-SOURCES = ["dense.cu", "ozaki.cu", "gpkern.cu", "api.cu", "lapack_api.cu", "host.cu", "modelio.cu", "dist.cu", "sparse.cu"]
+SOURCES = ["dense.cu", "ozaki.cu", "gpkern.cu", "api.cu", "lapack_api.cu", "host.cu", "modelio.cu", "dist.cu", "sparse.cu", "smpart.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "gpc_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

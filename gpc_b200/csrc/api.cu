@@ -293,18 +293,29 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
   return winv_offdiag(d, A, lda, n1, n2, base, T, t_done, t_ready);
 }
 
-int inverse_from_W(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, bool deferred_top) {
+// the deferred top-level W21 (no-op when nothing was deferred): after this W = L^-1 is complete
+int complete_W(const Dense& d, const double* L, int64_t ldl, int64_t n, bool deferred_top) {
   if (deferred_top && n > TILE) {
     int64_t n1 = split(n), n2 = n - n1;
     const cudaEvent_t t_ready = d.top_t_ready ? *d.top_t_ready : nullptr;  // T already queued by the factorisation?
     GPC_CHECK(winv_offdiag(d, L, ldl, n1, n2, 0, d.Tpool, t_ready != nullptr, t_ready));
     if (d.top_t_ready) *d.top_t_ready = nullptr;
   }
+  return GPC_OK;
+}
+
+// Out (lower triangle; mirrored into the upper one when `mirror`) = W' W = (L L')^-1 from the complete W
+int kinv_from_W(const Dense& d, int64_t n, double* Out, int64_t ldo, bool mirror) {
   // Out(i, j) = sum_{kk >= i} W(kk, i) W(kk, j), i >= j: lower tiles only, k starts at the tile's first row
   GemmCall g{d.Winv, d.Winv, Out, d.ldw, d.ldw, ldo, n, n, n, 1.0, 0.0, true, true, true};
   g.a_tri = +1;
   GPC_CHECK(gemm(d, g));
-  return launch_mirror_lower(Out, ldo, n, d.s, d.launches);
+  return mirror ? launch_mirror_lower(Out, ldo, n, d.s, d.launches) : GPC_OK;
+}
+
+int inverse_from_W(const Dense& d, const double* L, int64_t ldl, int64_t n, double* Out, int64_t ldo, bool deferred_top) {
+  GPC_CHECK(complete_W(d, L, ldl, n, deferred_top));
+  return kinv_from_W(d, n, Out, ldo, true);
 }
 
 }  // namespace gpc
@@ -337,6 +348,12 @@ struct gpc_ctx {
   double* hres;    // pinned host result buffer
   int* hinfo;      // pinned
   bool haveX, haveM, haveK, haveL, haveInv, haveAlpha;
+  // gpc_eval builds K straight into the buffer that is factored in place; the K buffer itself is rebuilt on demand
+  // (gpc_download, gpc_potrf, ...) from the kernel of that evaluation
+  bool k_lazy;
+  KSpec ks_last;
+  bool kinv_full;      // the upper triangle of K^-1 is a mirror of the lower one (gpc_eval leaves it unwritten)
+  double *zw, *trmv_part;  // alpha = W'(W m): the intermediate vector and the partial sums of the two products
   int64_t launches;
   cudaEvent_t ev[6];
   double last_ms[6];
@@ -387,6 +404,8 @@ static int ensure_inverse_buffers(gpc_ctx* c) {
   if (!c->use_winv && !c->W) GPC_CUDA_CHECK(cudaMalloc(&c->W, (potri_workspace(c->Npmax) + 16) * sizeof(double)));
   if (!c->symm_part)
     GPC_CUDA_CHECK(cudaMalloc(&c->symm_part, (size_t)symm_chunks(c->Npmax) * 4 * c->Npmax * sizeof(double)));
+  if (!c->zw) GPC_CUDA_CHECK(cudaMalloc(&c->zw, (size_t)c->Npmax * c->dmax * sizeof(double)));
+  if (!c->trmv_part) GPC_CUDA_CHECK(cudaMalloc(&c->trmv_part, (size_t)8 * 4 * c->Npmax * sizeof(double)));
   return GPC_OK;
 }
 
@@ -532,7 +551,7 @@ int gpc_ctx_destroy(gpc_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->X); cudaFree(c->M); cudaFree(c->alpha); cudaFree(c->K); cudaFree(c->L);
   cudaFree(c->Kinv); cudaFree(c->Winv); cudaFree(c->W); cudaFree(c->Dinv); cudaFree(c->scal); cudaFree(c->info);
-  cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->symm_part); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->Kc2); cudaFree(c->tmp1); cudaFree(c->tmp2);
+  cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->symm_part); cudaFree(c->zw); cudaFree(c->trmv_part); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->Kc2); cudaFree(c->tmp1); cudaFree(c->tmp2);
   cudaFreeHost(c->hres); cudaFreeHost(c->hinfo);
   gpc_ctx_set_profile(c, 0);
   if (c->fork) {
@@ -595,6 +614,7 @@ int gpc_set_X(gpc_ctx* c, const double* X, int64_t N, int D, int64_t ldx) {
   GPC_CHECK(upload(c, c->X, Np, X, ldx, N, D));
   c->haveX = true;
   c->haveK = c->haveL = c->haveInv = c->haveAlpha = false;
+  c->k_lazy = false;
   return GPC_OK;
 }
 
@@ -651,21 +671,33 @@ int gpc_kern_build(gpc_ctx* c, const gpc_kcomp* comps, int ncomp) {
   GPC_CHECK(make_kspec(comps, ncomp, c->D, &ks));
   GPC_CHECK(launch_kbuild(ks, c->X, c->Np, c->N, c->Np, c->K, c->Np, c->stream, &c->launches));
   c->haveK = true;
+  c->k_lazy = false;
   c->haveL = c->haveInv = c->haveAlpha = false;
   return GPC_OK;
 }
 
+// gpc_eval factors K in the buffer it was built in; whoever needs the K buffer afterwards gets it rebuilt here
+static int ensure_K(gpc_ctx* c) {
+  if (!c || c->haveK || !c->k_lazy || !c->haveX) return GPC_OK;
+  GPC_CHECK(launch_kbuild(c->ks_last, c->X, c->Np, c->N, c->Np, c->K, c->Np, c->stream, &c->launches));
+  c->haveK = true;
+  c->k_lazy = false;
+  return GPC_OK;
+}
+
 int gpc_add_diag(gpc_ctx* c, double jitter) {
+  GPC_CHECK(ensure_K(c));
   GPC_CHECK(need(c, c && c->haveK, "gpc_add_diag needs K"));
   GPC_CHECK(launch_add_diag(c->K, c->Np, c->N, jitter, c->stream, &c->launches));
   c->haveL = c->haveInv = c->haveAlpha = false;
   return GPC_OK;
 }
 
-static int potrf_async(gpc_ctx* c) {
+// in_place: the lower triangle of K is already in the L buffer (gpc_eval builds it there)
+static int potrf_async(gpc_ctx* c, bool in_place = false) {
   GPC_CUDA_CHECK(cudaMemsetAsync(c->info, 0, sizeof(int), c->stream));
   GPC_CUDA_CHECK(cudaMemsetAsync(c->scal + SC_LOGDET, 0, sizeof(double), c->stream));
-  GPC_CHECK(launch_copy_lower(c->K, c->Np, c->L, c->Np, c->Np, c->stream, &c->launches));
+  if (!in_place) GPC_CHECK(launch_copy_lower(c->K, c->Np, c->L, c->Np, c->Np, c->stream, &c->launches));
   if (c->use_winv) {
     GPC_CHECK(ensure_inverse_buffers(c));
     if (c->winv_np != c->Np) {
@@ -697,6 +729,7 @@ static int inverse_async(gpc_ctx* c) {
 }
 
 int gpc_potrf(gpc_ctx* c, int* info, double* logdet) {
+  GPC_CHECK(ensure_K(c));
   GPC_CHECK(need(c, c && c->haveK, "gpc_potrf needs K"));
   c->haveL = c->haveInv = c->haveAlpha = false;  // L is overwritten: valid again only if info == 0
   GPC_CHECK(potrf_async(c));
@@ -723,6 +756,7 @@ static int trace_K(gpc_ctx* c, double* tr) {
 }
 
 int gpc_jitchol(gpc_ctx* c, int max_tries, double* jitter_out, double* logdet) {
+  GPC_CHECK(ensure_K(c));
   GPC_CHECK(need(c, c && c->haveK, "gpc_jitchol needs K"));
   if (max_tries <= 0) max_tries = 20;  // CMatrix.h:1060 default
   double jitter = 0.0;
@@ -766,15 +800,29 @@ int gpc_inverse(gpc_ctx* c) {
   GPC_CHECK(ensure_inverse_buffers(c));
   GPC_CHECK(inverse_async(c));
   c->haveInv = true;
+  c->kinv_full = true;
   return GPC_OK;
 }
 
 static int alpha_from_inverse_async(gpc_ctx* c) {
+  if (!c->kinv_full) {  // the symmetric product reads whole rows
+    GPC_CHECK(launch_mirror_lower(c->Kinv, c->Np, c->Np, c->stream, &c->launches));
+    c->kinv_full = true;
+  }
   GPC_CUDA_CHECK(cudaMemsetAsync(c->scal + SC_QUAD, 0, sizeof(double), c->stream));
   // scratch for the column-chunk partial sums: the inverse workspace W is idle once K^-1 is complete
   GPC_CHECK(launch_symm_small(c->Kinv, c->Np, c->M, c->Np, c->alpha, c->Np, c->N, c->d, c->symm_part, c->stream,
                               &c->launches));
   return launch_dot(c->M, c->alpha, c->Np * c->d, c->scal + SC_QUAD, c->stream, &c->launches);
+}
+
+// alpha = W'(W m) and quad = m' alpha on stream s, straight from the (complete) triangular inverse: two HBM-bound
+// triangular matrix-vector products that do not wait for K^-1 = W'W
+static int alpha_from_W_async(gpc_ctx* c, cudaStream_t s) {
+  GPC_CUDA_CHECK(cudaMemsetAsync(c->scal + SC_QUAD, 0, sizeof(double), s));
+  GPC_CHECK(launch_trmv_lower(c->Winv, c->Np, false, c->M, c->Np, c->zw, c->Np, c->Np, c->d, c->trmv_part, s, &c->launches));
+  GPC_CHECK(launch_trmv_lower(c->Winv, c->Np, true, c->zw, c->Np, c->alpha, c->Np, c->Np, c->d, c->trmv_part, s, &c->launches));
+  return launch_dot(c->M, c->alpha, c->Np * c->d, c->scal + SC_QUAD, s, &c->launches);
 }
 
 int gpc_alpha_from_inverse(gpc_ctx* c, double* quad) {
@@ -1036,8 +1084,13 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
   c->haveL = c->haveInv = c->haveAlpha = false;
   const auto host_t0 = std::chrono::steady_clock::now();
   GPC_CUDA_CHECK(cudaEventRecord(c->ev[0], s));
-  GPC_CHECK(launch_kbuild(ks, c->X, c->Np, c->N, c->Np, c->K, c->Np, s, &c->launches));
-  c->haveK = true;
+  // K is built straight into the buffer that is factored in place (its lower triangle is all the factorisation reads);
+  // the K buffer itself is rebuilt only if somebody asks for it (ensure_K) or the jitter schedule needs to mutate it
+  GPC_CHECK(launch_kbuild(ks, c->X, c->Np, c->N, c->Np, c->L, c->Np, s, &c->launches));
+  c->haveK = false;
+  c->k_lazy = true;
+  c->ks_last = ks;
+  bool in_place = true;
   GPC_CUDA_CHECK(cudaEventRecord(c->ev[1], s));
   GPC_CHECK(trace_phase(c, "kbuild"));
   double jitter_used = 0.0;
@@ -1050,16 +1103,41 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
       c->prof->recs.clear();
     }
     c->inverse_follows = true;
-    int prc = potrf_async(c);
+    int prc = potrf_async(c, in_place);
     c->inverse_follows = false;
     GPC_CHECK(prc);
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[2], s));
     GPC_CHECK(trace_phase(c, "potrf"));
     // optimistic: queue the rest before looking at info (a failed factorisation is rare and just redone)
-    GPC_CHECK(inverse_async(c));
-    GPC_CUDA_CHECK(cudaEventRecord(c->ev[3], s));
-    GPC_CHECK(trace_phase(c, "inverse"));
-    GPC_CHECK(alpha_from_inverse_async(c));
+    if (c->use_winv) {
+      Dense dd = dense_of(c);
+      dd.top_t_ready = &c->top_t_ready;
+      GPC_CHECK(complete_W(dd, c->L, c->Np, c->Np, c->w_deferred));
+      c->w_deferred = false;
+      // alpha = W'(W m) needs W only: two HBM-bound products on a side stream, hidden behind the tensor-bound W'W
+      cudaEvent_t e_alpha = nullptr;
+      if (c->fork && !c->prof) {
+        cudaEvent_t e_w = c->fork->event();
+        e_alpha = c->fork->event();
+        cudaStream_t side = c->fork->stream();
+        GPC_CUDA_CHECK(cudaEventRecord(e_w, s));
+        GPC_CUDA_CHECK(cudaStreamWaitEvent(side, e_w, 0));
+        GPC_CHECK(alpha_from_W_async(c, side));
+        GPC_CUDA_CHECK(cudaEventRecord(e_alpha, side));
+      }
+      GPC_CHECK(kinv_from_W(dd, c->Np, c->Kinv, c->Np, false));  // lower triangle only: all the gradient pass reads
+      c->kinv_full = false;
+      GPC_CUDA_CHECK(cudaEventRecord(c->ev[3], s));
+      GPC_CHECK(trace_phase(c, "inverse"));
+      if (e_alpha) GPC_CUDA_CHECK(cudaStreamWaitEvent(s, e_alpha, 0));
+      else GPC_CHECK(alpha_from_W_async(c, s));
+    } else {
+      GPC_CHECK(inverse_async(c));
+      c->kinv_full = true;
+      GPC_CUDA_CHECK(cudaEventRecord(c->ev[3], s));
+      GPC_CHECK(trace_phase(c, "inverse"));
+      GPC_CHECK(alpha_from_inverse_async(c));
+    }
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[4], s));
     GPC_CHECK(trace_phase(c, "alpha"));
     GPC_CHECK(grad_async(c, ks, wantX));
@@ -1070,7 +1148,13 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
     c->enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     GPC_CUDA_CHECK(cudaStreamSynchronize(s));
     if (*c->hinfo == 0) break;
-    // jitChol schedule (CMatrix.cpp:767-804)
+    // jitChol schedule (CMatrix.cpp:767-804): from here on K lives in its own buffer and is mutated there
+    if (in_place) {
+      GPC_CHECK(launch_kbuild(ks, c->X, c->Np, c->N, c->Np, c->K, c->Np, s, &c->launches));
+      c->haveK = true;
+      c->k_lazy = false;
+      in_place = false;
+    }
     if (!have_trace) {
       double tr;
       GPC_CHECK(trace_K(c, &tr));
@@ -1183,6 +1267,7 @@ int gpc_download(gpc_ctx* c, int which, double* dst, int64_t ld) {
   int64_t N = c->N;
   switch (which) {
     case GPC_MAT_K:
+      GPC_CHECK(ensure_K(c));
       GPC_CHECK(need(c, c->haveK, "K not built"));
       GPC_CHECK(download(c, dst, ld, c->K, c->Np, N, N));
       for (int64_t j = 0; j < N; j++)
@@ -1196,7 +1281,11 @@ int gpc_download(gpc_ctx* c, int which, double* dst, int64_t ld) {
       return GPC_OK;
     case GPC_MAT_KINV:
       GPC_CHECK(need(c, c->haveInv, "K^-1 not available"));
-      return download(c, dst, ld, c->Kinv, c->Np, N, N);
+      GPC_CHECK(download(c, dst, ld, c->Kinv, c->Np, N, N));
+      if (!c->kinv_full)  // gpc_eval writes the lower triangle only
+        for (int64_t j = 0; j < N; j++)
+          for (int64_t i = 0; i < j; i++) dst[i + j * ld] = dst[j + i * ld];
+      return GPC_OK;
     case GPC_MAT_ALPHA:
       GPC_CHECK(need(c, c->haveAlpha, "alpha not available"));
       return download(c, dst, ld, c->alpha, c->Np, N, c->d);

@@ -31,6 +31,13 @@ int trace_sync(const char* what, cudaStream_t s);
     }                                                                                               \
   } while (0)
 
+// ---- SM partition (smpart.cu): a small "chain" set and a large "bulk" set of SMs (green contexts) --------------
+struct SmPartition;
+SmPartition* smpart_create(int device, int chain_sms, int dflt);  // null: switched off (GPC_SM_PARTITION=0) / unsupported
+void smpart_destroy(SmPartition* p);
+int smpart_sms(const SmPartition* p, bool chain);
+int smpart_stream(SmPartition* p, bool chain, int priority, cudaStream_t* out);
+
 // ---- kernel specification passed by value to the K-build / gradient kernels --------------------------
 struct KSpec {
   int ncomp;
@@ -114,6 +121,9 @@ int launch_set_identity_pad(double* A, int64_t lda, int64_t n, int64_t np, cudaS
 int symm_chunks(int64_t n);
 int launch_symm_small(const double* A, int64_t lda, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
                       int d, double* part, cudaStream_t s, int64_t* launches);
+// y = W x / W' x for a lower block-triangular W (block-upper part never read); part: scratch as for launch_symm_small
+int launch_trmv_lower(const double* W, int64_t ldw, bool trans, const double* x, int64_t ldx, double* y, int64_t ldy,
+                      int64_t n, int d, double* part, cudaStream_t s, int64_t* launches);
 int launch_dot(const double* x, const double* y, int64_t n, double* out, cudaStream_t s, int64_t* launches);
 
 // inverse of the lower-triangular TILE x TILE block at A (no factorisation): Dinv as above

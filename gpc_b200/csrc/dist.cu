@@ -253,6 +253,7 @@ struct DistRank {
   double *Wb = nullptr, *Lp = nullptr, *tmpL = nullptr, *Tpool = nullptr;
   double *Wb2 = nullptr, *LF[2] = {nullptr, nullptr};  // single-rank fast chain: second W_kk buffer, the fp64 tiles L_{k+1,k}
   cudaStream_t s_chain = nullptr;
+  SmPartition* part = nullptr;  // single rank: the chain stream owns a few SMs, the panel / main streams the rest
   int* emax = nullptr;
   uint8_t* slots[2] = {nullptr, nullptr};
   OzCycMaps maps[2];
@@ -332,10 +333,17 @@ static int rank_alloc(DistRank& r) {
   GPC_CUDA_CHECK(cudaMallocHost(&r.hres, (DS_G + GPC_MAX_PARAMS) * sizeof(double)));
   int lo = 0, hi = 0;
   GPC_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
-  GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_main, cudaStreamNonBlocking, lo));
-  GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_panel, cudaStreamNonBlocking, hi));
+  if (r.world == 1) r.part = smpart_create(r.device, 0, 0);
+  if (r.part) {
+    GPC_CHECK(smpart_stream(r.part, false, lo, &r.s_main));
+    GPC_CHECK(smpart_stream(r.part, false, hi, &r.s_panel));
+    GPC_CHECK(smpart_stream(r.part, true, hi, &r.s_chain));
+  } else {
+    GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_main, cudaStreamNonBlocking, lo));
+    GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_panel, cudaStreamNonBlocking, hi));
+    GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_chain, cudaStreamNonBlocking, hi));
+  }
   GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_comm, cudaStreamNonBlocking, hi));
-  GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&r.s_chain, cudaStreamNonBlocking, hi));
   r.ev.resize((size_t)8 * r.NBt + 8);
   for (auto& e : r.ev) GPC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int i = 0; i < 6; i++) GPC_CUDA_CHECK(cudaEventCreate(&r.tev[i]));
@@ -361,6 +369,8 @@ static void rank_free(DistRank& r) {
   if (r.s_panel) cudaStreamDestroy(r.s_panel);
   if (r.s_comm) cudaStreamDestroy(r.s_comm);
   if (r.s_chain) cudaStreamDestroy(r.s_chain);
+  smpart_destroy(r.part);
+  r.part = nullptr;
 }
 
 // Cholesky of the diagonal block (k, k) in place + its inverse into Wb: the single-GPU recursion on one nb x nb block
