@@ -119,6 +119,66 @@ def single_gpu_leg(G, name, device, reps=3):
     return out
 
 
+def concurrent_leg(G, name, device, nctx, steps, warmup=2):
+    """THROUGHPUT of `nctx` independent evaluations in flight on ONE GPU (one context + stream + host thread each: theta
+    candidates of a line search / restarts / the outputs of a multi-kernel model): the serial chain of one evaluation's
+    diagonal blocks runs under the tensor-core products of another.  Not the headline (an SCG run is sequential)."""
+    import threading
+    import torch
+    from gpc_b200._lib import check, lib, ptr
+    w = WORKLOADS[name]
+    N, D = w["N"], w["D"]
+    X, y, params = make_inputs(name)
+    workers = []
+    for i in range(nctx):
+        k = G.make_kern(w["types"], D)
+        k.setParams(params)
+        ctx = G.DeviceContext(N, D, 1, device=device)
+        st = torch.cuda.Stream(device=device)
+        ctx.set_stream(st.cuda_stream)
+        ctx.set_X(X)
+        ctx.set_M(y)
+        workers.append((k, ctx, st, k.getTransParams(), np.zeros(3), np.zeros(k.getNumParams())))
+    gate = threading.Barrier(nctx + 1)
+    errs = []
+
+    def run(i, n0, n):
+        k, ctx, st, tp0, out, g = workers[i]
+        try:
+            gate.wait()
+            for s in range(n):
+                k.setTransParams(theta_for_step(tp0, n0 + nctx * s + i))
+                arr, m, keep = k._kcomps()
+                rc = check(lib().gpc_eval(ctx.handle, arr, m, 0, ptr(out), ptr(g), None))
+                if rc != 0:
+                    raise RuntimeError("not positive definite (info=%d)" % rc)
+        except Exception as e:   # a failed worker must not leave the others waiting
+            errs.append(str(e))
+
+    def phase(n0, n):
+        th = [threading.Thread(target=run, args=(i, n0, n)) for i in range(nctx)]
+        for t in th:
+            t.start()
+        torch.cuda.synchronize()
+        gate.wait()
+        t0 = time.time()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        return time.time() - t0
+
+    phase(0, warmup)
+    dt = phase(1000, steps)
+    lls = [float(-0.5 * (wk[4][1] + wk[4][0]) - N * 0.5 * np.log(2 * np.pi)) for wk in workers]
+    for wk in workers:
+        wk[1].close()
+    if errs:
+        return {"error": errs[0]}
+    return {"contexts": nctx, "evals": nctx * steps, "seconds": dt, "evals_per_sec": nctx * steps / dt,
+            "ms_per_eval_amortised": 1e3 * dt / (nctx * steps), "ll_last": lls,
+            "timing": "host wall clock around the worker threads, device synchronised on both sides"}
+
+
 def sharded_leg(G, name, device, world, group, nb, reps=3):
     """one workload SHARDED over all ranks (gpc_dist_*: 2-D block-cyclic one-sweep K -> K^-1); host wall time around the
     collective call, max over ranks.  world == 1: the same algorithm on one GPU (one N^2 matrix resident)."""
@@ -588,6 +648,13 @@ def main():
                 also["c4"] = sharded_leg(G, "c4", local_rank, 1, None, nb=2048, reps=2)
             except Exception as e:
                 also["c4"] = {"error": str(e)}
+            # throughput with 2 / 3 independent C2 evaluations in flight on the one GPU
+            also["c2_concurrent"] = {}
+            for nc in (2, 3):
+                try:
+                    also["c2_concurrent"]["x%d" % nc] = concurrent_leg(G, "c2", local_rank, nc, max(4, args.steps // 2))
+                except Exception as e:
+                    also["c2_concurrent"]["x%d" % nc] = {"error": str(e)}
             for leg in also.values():
                 if "tflops_equiv" in leg and imma.value > 0:
                     leg["roofline_frac"] = leg["tflops_equiv"] / (imma.value / (S * (S + 1) / 2.0))
