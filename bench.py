@@ -24,6 +24,7 @@ import argparse
 import ctypes as C
 import json
 import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context exists (see gpc_b200/__init__.py)
 import subprocess
 import sys
 import tempfile

@@ -10,6 +10,12 @@
 #include <chrono>
 #include "common.cuh"
 
+// One evaluation uses ~20 streams (chain, bulk, side streams of the recursion).  With the default of 8 hardware work
+// queues several streams share a queue and a small chain kernel can sit behind the queued launches of a bulk product
+// on another stream (measured: 1 ms stalls, profiles/timeline_c2_r02.txt).  The driver reads the variable when the
+// context is created, so it is set when the library is loaded -- without overriding a value the user chose.
+__attribute__((constructor)) static void gpc_more_hw_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 namespace gpc {
 
 static thread_local std::string g_error;
@@ -40,7 +46,19 @@ int trace_sync(const char* what, cudaStream_t s) {
 static inline int64_t split(int64_t n) { return (n / TILE / 2) * TILE; }
 
 // every GEMM of the recursion goes through here so that profiling mode can bracket it with events
-static int gemm(const Dense& d, const GemmCall& g) {
+// SMs a bulk product may hold at a time while the serial chain of the factorisation runs next to it (GemmCall::sm_limit)
+static int bulk_sm_limit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GPC_BULK_SMS");
+    v = e ? atoi(e) : 132;
+  }
+  return v;
+}
+
+static int gemm(const Dense& d, const GemmCall& g0) {
+  GemmCall g = g0;
+  if (d.sm_limit > 0 && g.sm_limit == 0) g.sm_limit = d.sm_limit;
   if (!d.prof) return launch_gemm(g, d.s, d.launches);
   GemmProf* p = d.prof;
   if (p->used + 2 > p->ev.size()) {
@@ -255,6 +273,56 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
     GPC_CUDA_CHECK(cudaEventRecord(e_copy, side));
   }
   GPC_CHECK(potrf_inv_rec(d, A, lda, n1, base, T, false, tl_off + (size_t)n1 * n2));
+  TopPipe* tp = (d.tp && d.tp->on) ? d.tp : nullptr;
+  if (tp && defer_top) {
+    // row block 1 (W11) is complete: its contribution K^-1_11 = W11' W11 runs on the bulk stream under the rest
+    tp->n1 = n1;
+    tp->n2 = n2;
+    tp->y_queued = false;
+    GPC_CUDA_CHECK(cudaEventRecord(tp->e_w11, d.s));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(tp->bulk, tp->e_w11, 0));
+    Dense db = d;
+    db.s = tp->bulk;
+    db.sm_limit = bulk_sm_limit();
+    GemmCall g{W, W, tp->Kinv, d.ldw, d.ldw, tp->ldo, n1, n1, n1, 1.0, 0.0, true, true, true};
+    g.a_tri = +1;
+    GPC_CHECK(gemm(db, g));
+  } else if (tp && !defer_top && base == tp->n1 && n == tp->n2 && tp->t_ready) {
+    // second half of the top level, first diagonal node a' done (L and W of rows base .. base + n1):
+    //   Y1  W21[a', :] = -W_a'a' T[a', :]                                   (the top-level W21 is deferred: its rows a' now)
+    //   Y3  K^-1[<= a', <= a'] += W[a', <= a']' W[a', <= a']                  (three products: 11 block, a' row, a'a' block)
+    tp->h1 = n1;
+    const int64_t t1 = tp->n1, t2 = tp->n2, h1 = n1;
+    GPC_CUDA_CHECK(cudaEventRecord(tp->e_half, d.s));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(tp->bulk, tp->e_half, 0));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(tp->bulk, tp->t_ready, 0));
+    Dense db = d;
+    db.s = tp->bulk;
+    db.sm_limit = bulk_sm_limit();
+    double* Waa = d.Winv + t1 + t1 * d.ldw;  // W_a'a'
+    double* W21a = d.Winv + t1;              // rows a' of the top-level W21
+    {
+      GemmCall g{Waa, tp->T, W21a, d.ldw, t2, d.ldw, h1, t1, h1, -1.0, 0.0, false, true, false};
+      g.a_tri = -1;
+      GPC_CHECK(gemm(db, g));
+    }
+    {
+      GemmCall g{W21a, W21a, tp->Kinv, d.ldw, d.ldw, tp->ldo, t1, t1, h1, 1.0, 1.0, true, true, true};
+      GPC_CHECK(gemm(db, g));
+    }
+    {
+      GemmCall g{Waa, W21a, tp->Kinv + t1, d.ldw, d.ldw, tp->ldo, h1, t1, h1, 1.0, 0.0, true, true, false};
+      g.a_tri = +1;
+      GPC_CHECK(gemm(db, g));
+    }
+    {
+      GemmCall g{Waa, Waa, tp->Kinv + t1 + t1 * tp->ldo, d.ldw, d.ldw, tp->ldo, h1, h1, h1, 1.0, 0.0, true, true, true};
+      g.a_tri = +1;
+      GPC_CHECK(gemm(db, g));
+    }
+    GPC_CUDA_CHECK(cudaEventRecord(tp->e_bulk, tp->bulk));
+    tp->y_queued = true;
+  }
   if (e_copy) {  // W11'(kk, j) = W11(j, kk) is zero for kk > j: k ends at the tile's last column
     GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, e_copy, 0));
     GemmCall g{TL, W, A21, n2, d.ldw, lda, n2, n1, n1, 1.0, 0.0, false, false, false};
@@ -272,14 +340,26 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
     cudaEvent_t e1 = d.fk->event();
     t_ready = d.fk->event();
     Dense ds = d;
-    ds.s = d.fk->stream();
-    GPC_CUDA_CHECK(cudaEventRecord(e1, d.s));
-    GPC_CUDA_CHECK(cudaStreamWaitEvent(ds.s, e1, 0));
     GemmCall gt{A21, W, T, lda, d.ldw, n2, n2, n1, n1, 1.0, 0.0, false, true, false};
     gt.b_tri = +1;
+    // T is needed only for W21: it runs next to the chain of the A22 recursion.  A large one (tensor-core engine) goes
+    // to the ONE low-priority bulk stream, wave-limited so that the chain always finds free SMs; a small one to a
+    // (high-priority) side stream
+    if (d.bulk && oz_wants(gt)) {
+      ds.s = d.bulk;
+      ds.sm_limit = bulk_sm_limit();
+    } else {
+      ds.s = d.fk->stream();
+    }
+    GPC_CUDA_CHECK(cudaEventRecord(e1, d.s));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(ds.s, e1, 0));
     GPC_CHECK(gemm(ds, gt));
     GPC_CUDA_CHECK(cudaEventRecord(t_ready, ds.s));
     t_done = true;
+    if (tp && defer_top) {
+      tp->t_ready = t_ready;
+      tp->T = T;
+    }
   }
   {
     GemmCall g{A21, A21, A22, lda, lda, lda, n2, n2, n1, -1.0, 1.0, false, false, true};
@@ -295,6 +375,25 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
 
 // the deferred top-level W21 (no-op when nothing was deferred): after this W = L^-1 is complete
 int complete_W(const Dense& d, const double* L, int64_t ldl, int64_t n, bool deferred_top) {
+  if (deferred_top && d.tp && d.tp->on && d.tp->y_queued) {
+    // rows a' of the top-level W21 were done under the factorisation of b' (TopPipe); rows b' now:
+    //   W21[b', :] = -(W_b'a' T[a', :] + W_b'b' T[b', :])
+    const TopPipe& tp = *d.tp;
+    const int64_t t1 = tp.n1, t2 = tp.n2, h1 = tp.h1, h2 = t2 - h1;
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, tp.t_ready, 0));
+    double* C = d.Winv + t1 + h1;
+    {
+      GemmCall g{d.Winv + (t1 + h1) + t1 * d.ldw, tp.T, C, d.ldw, t2, d.ldw, h2, t1, h1, -1.0, 0.0, false, true, false};
+      GPC_CHECK(gemm(d, g));
+    }
+    {
+      GemmCall g{d.Winv + (t1 + h1) + (t1 + h1) * d.ldw, tp.T + h1, C, d.ldw, t2, d.ldw, h2, t1, h2, -1.0, 1.0, false, true, false};
+      g.a_tri = -1;
+      GPC_CHECK(gemm(d, g));
+    }
+    if (d.top_t_ready) *d.top_t_ready = nullptr;
+    return GPC_OK;
+  }
   if (deferred_top && n > TILE) {
     int64_t n1 = split(n), n2 = n - n1;
     const cudaEvent_t t_ready = d.top_t_ready ? *d.top_t_ready : nullptr;  // T already queued by the factorisation?
@@ -306,6 +405,31 @@ int complete_W(const Dense& d, const double* L, int64_t ldl, int64_t n, bool def
 
 // Out (lower triangle; mirrored into the upper one when `mirror`) = W' W = (L L')^-1 from the complete W
 int kinv_from_W(const Dense& d, int64_t n, double* Out, int64_t ldo, bool mirror) {
+  if (d.tp && d.tp->on && d.tp->y_queued && Out == d.tp->Kinv) {
+    // the contributions of the row blocks 1 and a' are (being) accumulated on the bulk stream; row block b' now:
+    //   K^-1[< b', < b'] += R'R,  K^-1[b', < b'] = W_b'b'' R,  K^-1[b', b'] = W_b'b'' W_b'b',   R = W[b', < b']
+    TopPipe& tp = *d.tp;
+    const int64_t t1 = tp.n1, h1 = tp.h1, h2 = tp.n2 - h1, m = t1 + h1;
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, tp.e_bulk, 0));
+    double* R = d.Winv + m;                  // rows b', columns 0 .. m-1
+    double* Wbb = d.Winv + m + m * d.ldw;    // W_b'b'
+    {
+      GemmCall g{R, R, Out, d.ldw, d.ldw, ldo, m, m, h2, 1.0, 1.0, true, true, true};
+      GPC_CHECK(gemm(d, g));
+    }
+    {
+      GemmCall g{Wbb, R, Out + m, d.ldw, d.ldw, ldo, h2, m, h2, 1.0, 0.0, true, true, false};
+      g.a_tri = +1;
+      GPC_CHECK(gemm(d, g));
+    }
+    {
+      GemmCall g{Wbb, Wbb, Out + m + m * ldo, d.ldw, d.ldw, ldo, h2, h2, h2, 1.0, 0.0, true, true, true};
+      g.a_tri = +1;
+      GPC_CHECK(gemm(d, g));
+    }
+    tp.y_queued = false;
+    return mirror ? launch_mirror_lower(Out, ldo, n, d.s, d.launches) : GPC_OK;
+  }
   // Out(i, j) = sum_{kk >= i} W(kk, i) W(kk, j), i >= j: lower tiles only, k starts at the tile's first row
   GemmCall g{d.Winv, d.Winv, Out, d.ldw, d.ldw, ldo, n, n, n, 1.0, 0.0, true, true, true};
   g.a_tri = +1;
@@ -354,6 +478,12 @@ struct gpc_ctx {
   KSpec ks_last;
   bool kinv_full;      // the upper triangle of K^-1 is a mirror of the lower one (gpc_eval leaves it unwritten)
   double *zw, *trmv_part;  // alpha = W'(W m): the intermediate vector and the partial sums of the two products
+  // gpc_eval: the factorisation runs on a high-priority stream (its serial chain of small kernels must not queue behind
+  // the CTAs of the side-stream products), the row-block pipeline of the top level on a low-priority one
+  cudaStream_t chain_stream, bulk_stream;
+  cudaEvent_t ev_pipe[6];   // chain fork / join, W11 ready, a' ready, bulk done, bulk joined
+  TopPipe pipe;
+  double* pipe_scratch;     // tmpL / Tpool / TLpool outside K^-1 (the pipeline writes K^-1 while they are in use)
   int64_t launches;
   cudaEvent_t ev[6];
   double last_ms[6];
@@ -384,9 +514,13 @@ static Dense dense_of(gpc_ctx* c) {
   d.Winv = c->Winv;
   d.top_t_ready = nullptr;
   d.ldw = c->Np;
-  // scratch inside the (not yet written) K^-1 buffer: tmpL then Tpool
-  d.tmpL = c->Kinv;
-  d.Tpool = c->Kinv ? c->Kinv + (size_t)(c->Npmax / 2 + TILE) * (size_t)(c->Npmax / 2 + TILE) : nullptr;
+  d.tp = &c->pipe;
+  d.bulk = (c->stream == c->chain_stream) ? c->bulk_stream : nullptr;  // only while gpc_eval runs the chain at priority
+  // scratch inside the (not yet written) K^-1 buffer: tmpL then Tpool -- or in its own buffer when the row-block
+  // pipeline may write K^-1 during the factorisation
+  double* scr = c->pipe_scratch ? c->pipe_scratch : c->Kinv;
+  d.tmpL = scr;
+  d.Tpool = scr ? scr + (size_t)(c->Npmax / 2 + TILE) * (size_t)(c->Npmax / 2 + TILE) : nullptr;
   d.TLpool = d.Tpool ? d.Tpool + potrf_inv_tspace(c->Npmax) + 16 : nullptr;
   return d;
 }
@@ -404,6 +538,13 @@ static int ensure_inverse_buffers(gpc_ctx* c) {
   if (!c->use_winv && !c->W) GPC_CUDA_CHECK(cudaMalloc(&c->W, (potri_workspace(c->Npmax) + 16) * sizeof(double)));
   if (!c->symm_part)
     GPC_CUDA_CHECK(cudaMalloc(&c->symm_part, (size_t)symm_chunks(c->Npmax) * 4 * c->Npmax * sizeof(double)));
+  {
+    // off by default: measured on B200 at C2 (profiles/timeline_c2_r02.txt) the bulk products slow the chain's own
+    // mid-size products by more than the shorter tail returns (13.4 vs 12.4 ms); GPC_TOP_PIPE=1 switches it on
+    const char* e = getenv("GPC_TOP_PIPE");
+    const bool want = c->use_winv && c->fork && c->Npmax >= 1024 && c->Npmax <= 16384 && e && atoi(e) != 0;
+    if (want && !c->pipe_scratch) GPC_CUDA_CHECK(cudaMalloc(&c->pipe_scratch, scratch * sizeof(double)));
+  }
   if (!c->zw) GPC_CUDA_CHECK(cudaMalloc(&c->zw, (size_t)c->Npmax * c->dmax * sizeof(double)));
   if (!c->trmv_part) GPC_CUDA_CHECK(cudaMalloc(&c->trmv_part, (size_t)8 * 4 * c->Npmax * sizeof(double)));
   return GPC_OK;
@@ -533,13 +674,23 @@ static int ctx_create_impl(gpc_ctx* c, int device, int64_t Nmax, int Dmax, int d
   GPC_CUDA_CHECK(cudaMemset(c->M, 0, np * dout_max * sizeof(double)));
   GPC_CUDA_CHECK(cudaMemset(c->alpha, 0, np * dout_max * sizeof(double)));
   for (int i = 0; i < 6; i++) GPC_CUDA_CHECK(cudaEventCreate(&c->ev[i]));
+  {
+    int lo = 0, hi = 0;
+    GPC_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
+    GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&c->chain_stream, cudaStreamNonBlocking, hi));
+    GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&c->bulk_stream, cudaStreamNonBlocking, lo));
+    for (int i = 0; i < 6; i++) GPC_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_pipe[i], cudaEventDisableTiming));
+  }
   if (!getenv("GPC_NO_FORK")) {
     c->fork = new Fork();
     c->fork->side.resize(16);
     // two events per node of the recursions, N/128 - 1 nodes each: the round-robin pool must not wrap inside one
     // evaluation (a re-recorded event would redirect a wait that has not been queued yet)
     c->fork->ev.resize((size_t)(8 * (c->Npmax / TILE) + 512));
-    for (auto& st : c->fork->side) GPC_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    // the side streams carry pieces of the factorisation's own chain (panel copies, small products): chain priority
+    int lo = 0, hi = 0;
+    GPC_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (auto& st : c->fork->side) GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
     for (auto& e : c->fork->ev) GPC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   return GPC_OK;
@@ -551,7 +702,7 @@ int gpc_ctx_destroy(gpc_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->X); cudaFree(c->M); cudaFree(c->alpha); cudaFree(c->K); cudaFree(c->L);
   cudaFree(c->Kinv); cudaFree(c->Winv); cudaFree(c->W); cudaFree(c->Dinv); cudaFree(c->scal); cudaFree(c->info);
-  cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->symm_part); cudaFree(c->zw); cudaFree(c->trmv_part); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->Kc2); cudaFree(c->tmp1); cudaFree(c->tmp2);
+  cudaFree(c->partial); cudaFree(c->gXdev); cudaFree(c->symm_part); cudaFree(c->zw); cudaFree(c->trmv_part); cudaFree(c->pipe_scratch); cudaFree(c->Xs); cudaFree(c->Kc); cudaFree(c->Kc2); cudaFree(c->tmp1); cudaFree(c->tmp2);
   cudaFreeHost(c->hres); cudaFreeHost(c->hinfo);
   gpc_ctx_set_profile(c, 0);
   if (c->fork) {
@@ -563,6 +714,10 @@ int gpc_ctx_destroy(gpc_ctx* c) {
   }
   for (int i = 0; i < 6; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 6; i++)
+    if (c->ev_pipe[i]) cudaEventDestroy(c->ev_pipe[i]);
+  if (c->chain_stream) cudaStreamDestroy(c->chain_stream);
+  if (c->bulk_stream) cudaStreamDestroy(c->bulk_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return GPC_OK;
@@ -732,6 +887,7 @@ int gpc_potrf(gpc_ctx* c, int* info, double* logdet) {
   GPC_CHECK(ensure_K(c));
   GPC_CHECK(need(c, c && c->haveK, "gpc_potrf needs K"));
   c->haveL = c->haveInv = c->haveAlpha = false;  // L is overwritten: valid again only if info == 0
+  c->pipe.on = false;
   GPC_CHECK(potrf_async(c));
   GPC_CUDA_CHECK(cudaMemcpyAsync(c->hinfo, c->info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1102,9 +1258,35 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
       c->prof->flops.clear();
       c->prof->recs.clear();
     }
+    // the factorisation on the high-priority chain stream; the row-block pipeline of the top level (TopPipe) on the
+    // low-priority bulk stream when its scratch exists (N <= 16384) and the second half is not a single diagonal block
+    static const int chain_prio = getenv("GPC_CHAIN_PRIO") ? atoi(getenv("GPC_CHAIN_PRIO")) : 1;
+    const bool hp = chain_prio && c->use_winv && c->fork && !c->prof && c->chain_stream;
+    const bool pipe = hp && c->pipe_scratch && c->bulk_stream && c->Np >= 1024;
+    c->pipe.on = pipe;
+    c->pipe.y_queued = false;
+    c->pipe.t_ready = nullptr;
+    c->pipe.Kinv = c->Kinv;
+    c->pipe.ldo = c->Np;
+    c->pipe.bulk = c->bulk_stream;
+    c->pipe.e_w11 = c->ev_pipe[2];
+    c->pipe.e_half = c->ev_pipe[3];
+    c->pipe.e_bulk = c->ev_pipe[4];
+    if (hp) {
+      GPC_CUDA_CHECK(cudaEventRecord(c->ev_pipe[0], s));
+      GPC_CUDA_CHECK(cudaStreamWaitEvent(c->chain_stream, c->ev_pipe[0], 0));
+      c->stream = c->chain_stream;
+    }
     c->inverse_follows = true;
     int prc = potrf_async(c, in_place);
     c->inverse_follows = false;
+    if (hp) {
+      c->stream = s;
+      if (prc == GPC_OK) {
+        GPC_CUDA_CHECK(cudaEventRecord(c->ev_pipe[1], c->chain_stream));
+        GPC_CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pipe[1], 0));
+      }
+    }
     GPC_CHECK(prc);
     GPC_CUDA_CHECK(cudaEventRecord(c->ev[2], s));
     GPC_CHECK(trace_phase(c, "potrf"));
@@ -1119,13 +1301,19 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
       if (c->fork && !c->prof) {
         cudaEvent_t e_w = c->fork->event();
         e_alpha = c->fork->event();
-        cudaStream_t side = c->fork->stream();
+        // low priority: the two products must not take SMs from the W'W product they hide behind
+        cudaStream_t side = c->bulk_stream ? c->bulk_stream : c->fork->stream();
         GPC_CUDA_CHECK(cudaEventRecord(e_w, s));
         GPC_CUDA_CHECK(cudaStreamWaitEvent(side, e_w, 0));
         GPC_CHECK(alpha_from_W_async(c, side));
         GPC_CUDA_CHECK(cudaEventRecord(e_alpha, side));
       }
+      if (pipe) {  // whatever the pipeline queued on the bulk stream writes K^-1: join it before the rest is added
+        GPC_CUDA_CHECK(cudaEventRecord(c->ev_pipe[5], c->bulk_stream));
+        GPC_CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pipe[5], 0));
+      }
       GPC_CHECK(kinv_from_W(dd, c->Np, c->Kinv, c->Np, false));  // lower triangle only: all the gradient pass reads
+      c->pipe.on = false;
       c->kinv_full = false;
       GPC_CUDA_CHECK(cudaEventRecord(c->ev[3], s));
       GPC_CHECK(trace_phase(c, "inverse"));

@@ -71,6 +71,11 @@ struct GemmCall {
   //   a_tri = +1: opA(A)(i, kk) == 0 for kk < i (same as ktri);  a_tri = -1: == 0 for kk > i
   //   b_tri = +1: opB(B)(kk, j) == 0 for kk < j;                  b_tri = -1: == 0 for kk > j
   int a_tri = 0, b_tri = 0;
+  // > 0: at most this many SMs at a time for a product on the tensor-core engine (it is launched wave by wave, each
+  // launch holding <= sm_limit resident CTAs): bulk products that run NEXT TO the serial chain of the factorisation
+  // leave the other SMs free for it -- a tile owns its SM for ~50 us, and stream priorities alone do not help a chain
+  // of small kernels that needs a free SM every few microseconds
+  int sm_limit = 0;
 };
 int launch_gemm(const GemmCall& g, cudaStream_t s, int64_t* launches);
 void gemm_force_config(int cfg);  // -1: heuristic (default); 0..4: force a DMMA tile configuration; 100+S: Ozaki, S slices
@@ -148,7 +153,23 @@ struct Fork {  // side streams + events for fork/join concurrency inside the rec
   size_t next_c = 0;
   cudaEvent_t event() { return ev[next_e++ % ev.size()]; }
 };
+// Row-block pipeline of the TOP level of potrf_inv_rec when the inverse follows (gpc_eval): the second half of the
+// matrix is factored as two diagonal nodes a', b'; as soon as a diagonal node is done, the rows of W = L^-1 of that row
+// block and their contribution to K^-1 = W'W are queued on a low-priority bulk stream, where they run under the serial
+// chain of the next diagonal node instead of after the whole factorisation (api.cu)
+struct TopPipe {
+  bool on = false, y_queued = false;
+  int64_t n1 = 0, n2 = 0, h1 = 0;  // top-level split; rows of a' (split of the second half)
+  double* Kinv = nullptr;
+  int64_t ldo = 0;
+  double* T = nullptr;             // top-level T = L21 W11 (n2 x n1, ld n2)
+  cudaStream_t bulk = nullptr;
+  cudaEvent_t e_w11 = nullptr, e_half = nullptr, e_bulk = nullptr, t_ready = nullptr;
+};
 struct Dense {
+  TopPipe* tp = nullptr;
+  int sm_limit = 0;    // copied into every product issued through this view (GemmCall::sm_limit)
+  cudaStream_t bulk = nullptr;  // low-priority stream for large products that run next to the chain (null: side streams)
   GemmProf* prof = nullptr;
   Fork* fk = nullptr;  // null: everything on `s`
   cudaStream_t s;

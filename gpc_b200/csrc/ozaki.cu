@@ -286,6 +286,7 @@ struct OzArgs {
   int lower;             // skip tiles strictly above the diagonal
   int a_tri, b_tri;      // triangular operands: +1 zero for kk < row/col (k loop starts there), -1 zero for kk > row/col
   int kb_lo, kb_hi;      // k-block range of this launch (k is chunked so that the int32 levels cannot overflow)
+  int tile_base;         // first linear tile index of this launch (wave-by-wave launches, GemmCall::sm_limit)
   int RpadA, RpadB;      // padded row counts (slice stride in the tensor maps)
   int* errflag;
   // ---- block-cyclic one-sweep mode (dist.cu): C is the LOCAL part of a matrix distributed in nb x nb blocks over a
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   int bm, bn;
   {
     const int GM = 8;
-    const int t = blockIdx.x;
+    const int t = (int)blockIdx.x + a.tile_base;
     const int per_group = GM * a.tiles_n;
     const int grp = t / per_group, rem = t % per_group;
     const int first = grp * GM;
@@ -655,7 +656,7 @@ struct OzWorkspace {
   bool used = false;
 };
 static std::mutex g_oz_mu;
-constexpr int OZ_BIG = 2;  // two large calls (e.g. main stream + one side stream) may be in flight
+constexpr int OZ_BIG = 4;  // large calls in flight: main (chain) stream, a side stream (T), the bulk stream of the row-block pipeline
 static OzWorkspace g_oz_ws[64][OZ_BIG];
 static unsigned g_oz_big_next[64];
 // Calls whose slices fit OZ_SMALL_BYTES per operand take one of OZ_POOL fixed-size workspaces round-robin instead (each
@@ -800,8 +801,22 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   // the second large workspace only for operands up to 1 GB of slices: beyond that (N >= 32768) large calls are
   // serialised through one workspace, which keeps N = 65536 within one GPU's memory
   const bool rotate_big = op_bytes <= ((size_t)1 << 30);
-  OzWorkspace& w = shared_ws ? g_oz_ws[dev][rotate_big ? (g_oz_big_next[dev]++ % OZ_BIG) : 0]
-                             : g_oz_pool[dev][g_oz_pool_next[dev]++ % OZ_POOL];
+  // a workspace whose previous user has finished is preferred over plain rotation: a call on the (high-priority) chain
+  // stream must not queue behind a long product of the bulk stream just because the rotation pointed at its buffers
+  auto pick = [&](OzWorkspace* ws, int count, unsigned& next) -> OzWorkspace& {
+    for (int t = 0; t < count; t++) {
+      OzWorkspace& c = ws[(next + t) % count];
+      const bool idle = !c.used || cudaEventQuery(c.done) == cudaSuccess;
+      if (!idle) cudaGetLastError();  // cudaErrorNotReady is not an error
+      if (idle) {
+        next = (next + t + 1) % count;
+        return c;
+      }
+    }
+    return ws[next++ % count];
+  };
+  OzWorkspace& w = shared_ws ? (rotate_big ? pick(g_oz_ws[dev], OZ_BIG, g_oz_big_next[dev]) : g_oz_ws[dev][0])
+                             : pick(g_oz_pool[dev], OZ_POOL, g_oz_pool_next[dev]);
   if (!shared_ws && !w.sl[0]) {  // first small call on this device: allocate the whole pool now, not over 8 calls
     for (int q = 0; q < OZ_POOL; q++)
       for (int i = 0; i < 2; i++) GPC_CHECK(ensure_ws(g_oz_pool[dev][q], i, OZ_SMALL_BYTES, OZ_SMALL_ROWS));
@@ -845,10 +860,40 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   // |d| <= 128: (6 * 2^14 + 2 * 65 * 128) * k < 2^31  ->  k <= 18683: chunks of 128 k-blocks (16384)
   const int kchunk = 128;
   const double beta0 = c.beta;
+  // wave-by-wave launches (GemmCall::sm_limit): cut the linear tile range (grouped raster: groups of 8 row tiles, column
+  // by column) at column boundaries so that no launch holds more than sm_limit NON-EMPTY tiles (lower mode: a tile
+  // (bm, bn) exists iff bn <= 2 bm + 1; the others exit at once)
+  std::vector<int64_t> cuts;
+  cuts.push_back(0);
+  if (c.sm_limit > 0 && ntiles > c.sm_limit) {
+    const int GM = 8;
+    int64_t live = 0;
+    for (int first = 0; first < a.tiles_m; first += GM) {
+      const int gsz = (a.tiles_m - first) < GM ? (a.tiles_m - first) : GM;
+      const int64_t gbase = (int64_t)(first / GM) * GM * a.tiles_n;
+      for (int bn = 0; bn < a.tiles_n; bn++) {
+        int cnt = gsz;
+        if (a.lower) {
+          cnt = 0;
+          for (int r = 0; r < gsz; r++) cnt += (bn <= 2 * (first + r) + 1) ? 1 : 0;
+        }
+        if (live + cnt > c.sm_limit && live > 0) {
+          cuts.push_back(gbase + (int64_t)bn * gsz);
+          live = 0;
+        }
+        live += cnt;
+      }
+    }
+  }
+  cuts.push_back(ntiles);
   for (int kb = 0; kb < a.kblocks; kb += kchunk) {
     a.kb_lo = kb;
     a.kb_hi = (kb + kchunk < a.kblocks) ? kb + kchunk : a.kblocks;
     a.beta = (kb == 0) ? beta0 : 1.0;
+   for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+    a.tile_base = (int)cuts[ci];
+    const int64_t nlaunch = cuts[ci + 1] - cuts[ci];
+    if (nlaunch <= 0) continue;
     switch (S) {
 #define OZ_CASE(SS)                                                                                              \
   case SS: {                                                                                                     \
@@ -858,7 +903,7 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
       GPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem(SS))); \
       configured_dev[cur_device() & 63] = true;                                                                                         \
     }                                                                                                            \
-    kern<<<(unsigned)ntiles, OZ_THREADS, oz_smem(SS), s>>>(tmA, tmB, a);                                         \
+    kern<<<(unsigned)nlaunch, OZ_THREADS, oz_smem(SS), s>>>(tmA, tmB, a);                                        \
   } break;
       OZ_CASE(2) OZ_CASE(3) OZ_CASE(4) OZ_CASE(5) OZ_CASE(6) OZ_CASE(7) OZ_CASE(8)
 #undef OZ_CASE
@@ -867,6 +912,7 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
         return GPC_ERR_ARG;
     }
     if (launches) (*launches)++;
+   }
   }
   GPC_CUDA_CHECK(cudaGetLastError());
   GPC_CUDA_CHECK(cudaEventRecord(w.done, s));
