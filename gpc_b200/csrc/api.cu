@@ -272,7 +272,45 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
     GPC_CHECK(launch_copy_block(A21, lda, TL, n2, n2, n1, 1.0, side, d.launches));
     GPC_CUDA_CHECK(cudaEventRecord(e_copy, side));
   }
+  TopFront* tf = (d.tf && d.tf->on && d.bulk) ? d.tf : nullptr;
+  if (tf && defer_top) {  // announce the top-level panel to the A11 node (hook below)
+    tf->queued = false;
+    if (e_copy && n1 >= 8 * TILE) {
+      tf->n1 = n1;
+      tf->n2 = n2;
+      tf->lda = lda;
+      tf->A21 = A21;
+      tf->A22 = A22;
+      tf->TL = TL;
+      tf->e_copy = e_copy;
+    } else {
+      tf->n1 = 0;
+    }
+  }
   GPC_CHECK(potrf_inv_rec(d, A, lda, n1, base, T, false, tl_off + (size_t)n1 * n2));
+  if (tf && !defer_top && base == 0 && tf->n1 > 0 && n == tf->n1) {
+    // the A11 node of the top level, its first diagonal node a (h = n1 rows) done:
+    //   X1  L21[:, a] = A21[:, a] W_aa'        X2  A22 -= L21[:, a] L21[:, a]'       on the bulk stream, wave-limited
+    tf->h = n1;
+    GPC_CUDA_CHECK(cudaEventRecord(tf->e_a, d.s));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.bulk, tf->e_a, 0));
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.bulk, tf->e_copy, 0));
+    Dense db = d;
+    db.s = d.bulk;
+    db.sm_limit = bulk_sm_limit();
+    {
+      GemmCall g{tf->TL, d.Winv, tf->A21, tf->n2, d.ldw, tf->lda, tf->n2, n1, n1, 1.0, 0.0, false, false, false};
+      g.b_tri = -1;
+      GPC_CHECK(gemm(db, g));
+    }
+    {
+      GemmCall g{tf->A21, tf->A21, tf->A22, tf->lda, tf->lda, tf->lda, tf->n2, tf->n2, n1, -1.0, 1.0, false, false, true};
+      GPC_CHECK(gemm(db, g));
+    }
+    GPC_CUDA_CHECK(cudaEventRecord(tf->e_x2, d.bulk));
+    tf->queued = true;
+  }
+  const bool front = tf && defer_top && tf->queued;
   TopPipe* tp = (d.tp && d.tp->on) ? d.tp : nullptr;
   if (tp && defer_top) {
     // row block 1 (W11) is complete: its contribution K^-1_11 = W11' W11 runs on the bulk stream under the rest
@@ -323,7 +361,21 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
     GPC_CUDA_CHECK(cudaEventRecord(tp->e_bulk, tp->bulk));
     tp->y_queued = true;
   }
-  if (e_copy) {  // W11'(kk, j) = W11(j, kk) is zero for kk > j: k ends at the tile's last column
+  if (front) {
+    // the a-columns of L21 are (being) done on the bulk stream; the b-columns now:
+    //   L21[:, b] = A21[:, a] W_ba' + A21[:, b] W_bb'
+    const int64_t h = tf->h, hb = n1 - h;
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, e_copy, 0));
+    {
+      GemmCall g{TL, d.Winv + h, A21 + h * lda, n2, d.ldw, lda, n2, hb, h, 1.0, 0.0, false, false, false};
+      GPC_CHECK(gemm(d, g));
+    }
+    {
+      GemmCall g{TL + h * n2, d.Winv + h + h * d.ldw, A21 + h * lda, n2, d.ldw, lda, n2, hb, hb, 1.0, 1.0, false, false, false};
+      g.b_tri = -1;
+      GPC_CHECK(gemm(d, g));
+    }
+  } else if (e_copy) {  // W11'(kk, j) = W11(j, kk) is zero for kk > j: k ends at the tile's last column
     GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, e_copy, 0));
     GemmCall g{TL, W, A21, n2, d.ldw, lda, n2, n1, n1, 1.0, 0.0, false, false, false};
     g.b_tri = -1;
@@ -361,7 +413,13 @@ int potrf_inv_rec(const Dense& d, double* A, int64_t lda, int64_t n, int64_t bas
       tp->T = T;
     }
   }
-  {
+  if (front) {  // the a-columns' share of the update is on the bulk stream: wait for it, then the b-columns' share
+    const int64_t h = tf->h, hb = n1 - h;
+    GPC_CUDA_CHECK(cudaStreamWaitEvent(d.s, tf->e_x2, 0));
+    GemmCall g{A21 + h * lda, A21 + h * lda, A22, lda, lda, lda, n2, n2, hb, -1.0, 1.0, false, false, true};
+    GPC_CHECK(gemm(d, g));
+    tf->queued = false;
+  } else {
     GemmCall g{A21, A21, A22, lda, lda, lda, n2, n2, n1, -1.0, 1.0, false, false, true};
     GPC_CHECK(gemm(d, g));
   }
@@ -483,6 +541,8 @@ struct gpc_ctx {
   cudaStream_t chain_stream, bulk_stream;
   cudaEvent_t ev_pipe[6];   // chain fork / join, W11 ready, a' ready, bulk done, bulk joined
   TopPipe pipe;
+  TopFront front;
+  cudaEvent_t ev_front[2];
   double* pipe_scratch;     // tmpL / Tpool / TLpool outside K^-1 (the pipeline writes K^-1 while they are in use)
   int64_t launches;
   cudaEvent_t ev[6];
@@ -515,6 +575,7 @@ static Dense dense_of(gpc_ctx* c) {
   d.top_t_ready = nullptr;
   d.ldw = c->Np;
   d.tp = &c->pipe;
+  d.tf = &c->front;
   d.bulk = (c->stream == c->chain_stream) ? c->bulk_stream : nullptr;  // only while gpc_eval runs the chain at priority
   // scratch inside the (not yet written) K^-1 buffer: tmpL then Tpool -- or in its own buffer when the row-block
   // pipeline may write K^-1 during the factorisation
@@ -680,6 +741,7 @@ static int ctx_create_impl(gpc_ctx* c, int device, int64_t Nmax, int Dmax, int d
     GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&c->chain_stream, cudaStreamNonBlocking, hi));
     GPC_CUDA_CHECK(cudaStreamCreateWithPriority(&c->bulk_stream, cudaStreamNonBlocking, lo));
     for (int i = 0; i < 6; i++) GPC_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_pipe[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) GPC_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_front[i], cudaEventDisableTiming));
   }
   if (!getenv("GPC_NO_FORK")) {
     c->fork = new Fork();
@@ -716,6 +778,8 @@ int gpc_ctx_destroy(gpc_ctx* c) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 6; i++)
     if (c->ev_pipe[i]) cudaEventDestroy(c->ev_pipe[i]);
+  for (int i = 0; i < 2; i++)
+    if (c->ev_front[i]) cudaEventDestroy(c->ev_front[i]);
   if (c->chain_stream) cudaStreamDestroy(c->chain_stream);
   if (c->bulk_stream) cudaStreamDestroy(c->bulk_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -888,6 +952,7 @@ int gpc_potrf(gpc_ctx* c, int* info, double* logdet) {
   GPC_CHECK(need(c, c && c->haveK, "gpc_potrf needs K"));
   c->haveL = c->haveInv = c->haveAlpha = false;  // L is overwritten: valid again only if info == 0
   c->pipe.on = false;
+  c->front.on = false;
   GPC_CHECK(potrf_async(c));
   GPC_CUDA_CHECK(cudaMemcpyAsync(c->hinfo, c->info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA_CHECK(cudaMemcpyAsync(c->hres, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1261,7 +1326,8 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
     // the factorisation on the high-priority chain stream; the row-block pipeline of the top level (TopPipe) on the
     // low-priority bulk stream when its scratch exists (N <= 16384) and the second half is not a single diagonal block
     static const int chain_prio = getenv("GPC_CHAIN_PRIO") ? atoi(getenv("GPC_CHAIN_PRIO")) : 1;
-    const bool hp = chain_prio && c->use_winv && c->fork && !c->prof && c->chain_stream;
+    // (where the factorisation is latency-bound: beyond N = 16384 the large products own the GPU anyway)
+    const bool hp = chain_prio && c->use_winv && c->fork && !c->prof && c->chain_stream && c->Np <= 16384;
     const bool pipe = hp && c->pipe_scratch && c->bulk_stream && c->Np >= 1024;
     c->pipe.on = pipe;
     c->pipe.y_queued = false;
@@ -1272,6 +1338,12 @@ int gpc_eval(gpc_ctx* c, const gpc_kcomp* comps, int ncomp, int flags, double* o
     c->pipe.e_w11 = c->ev_pipe[2];
     c->pipe.e_half = c->ev_pipe[3];
     c->pipe.e_bulk = c->ev_pipe[4];
+    static const int top_front = getenv("GPC_TOP_FRONT") ? atoi(getenv("GPC_TOP_FRONT")) : 1;
+    c->front.on = hp && top_front && c->bulk_stream;
+    c->front.queued = false;
+    c->front.n1 = 0;
+    c->front.e_a = c->ev_front[0];
+    c->front.e_x2 = c->ev_front[1];
     if (hp) {
       GPC_CUDA_CHECK(cudaEventRecord(c->ev_pipe[0], s));
       GPC_CUDA_CHECK(cudaStreamWaitEvent(c->chain_stream, c->ev_pipe[0], 0));

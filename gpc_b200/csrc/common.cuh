@@ -166,8 +166,19 @@ struct TopPipe {
   cudaStream_t bulk = nullptr;
   cudaEvent_t e_w11 = nullptr, e_half = nullptr, e_bulk = nullptr, t_ready = nullptr;
 };
+// Look-ahead of the TOP level of potrf_inv_rec (gpc_eval): A11 is factored as two diagonal nodes a, b; as soon as a is
+// done, the a-columns of L21 = A21 W11' and their share of the trailing update A22 -= L21 L21' run on the bulk stream
+// under the serial chain of b, and only the b-columns are left on the critical path after A11 (api.cu)
+struct TopFront {
+  bool on = false, queued = false;
+  int64_t n1 = 0, n2 = 0, h = 0, lda = 0;
+  double *A21 = nullptr, *A22 = nullptr;
+  const double* TL = nullptr;   // copy of A21 (n2 x n1, ld n2)
+  cudaEvent_t e_copy = nullptr, e_a = nullptr, e_x2 = nullptr;
+};
 struct Dense {
   TopPipe* tp = nullptr;
+  TopFront* tf = nullptr;
   int sm_limit = 0;    // copied into every product issued through this view (GemmCall::sm_limit)
   cudaStream_t bulk = nullptr;  // low-priority stream for large products that run next to the chain (null: side streams)
   GemmProf* prof = nullptr;

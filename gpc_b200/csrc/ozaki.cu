@@ -659,6 +659,10 @@ static std::mutex g_oz_mu;
 constexpr int OZ_BIG = 4;  // large calls in flight: main (chain) stream, a side stream (T), the bulk stream of the row-block pipeline
 static OzWorkspace g_oz_ws[64][OZ_BIG];
 static unsigned g_oz_big_next[64];
+// high-water marks (bytes of slices, rows) of the large workspaces of a device: a workspace that has to grow grows to
+// the mark at once, so that after the first evaluation no call re-allocates (cudaFree synchronises the device), whichever
+// workspace the idle-first selection hands it
+static size_t g_oz_big_hw_bytes[64], g_oz_big_hw_rows[64];
 // Calls whose slices fit OZ_SMALL_BYTES per operand take one of OZ_POOL fixed-size workspaces round-robin instead (each
 // guarded by its own event), so that the concurrent branches of the recursions (fork/join side streams) do not
 // serialise on the shared buffers.  The pool is allocated once per device: no allocation in steady state.
@@ -803,15 +807,27 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   const bool rotate_big = op_bytes <= ((size_t)1 << 30);
   // a workspace whose previous user has finished is preferred over plain rotation: a call on the (high-priority) chain
   // stream must not queue behind a long product of the bulk stream just because the rotation pointed at its buffers
+  // ... and among the idle ones a workspace that is already large enough (growing one is a cudaFree + cudaMalloc, i.e.
+  // a device synchronisation in the middle of an evaluation)
   auto pick = [&](OzWorkspace* ws, int count, unsigned& next) -> OzWorkspace& {
+    int idle_any = -1;
     for (int t = 0; t < count; t++) {
-      OzWorkspace& c = ws[(next + t) % count];
+      const int i = (int)((next + t) % count);
+      OzWorkspace& c = ws[i];
       const bool idle = !c.used || cudaEventQuery(c.done) == cudaSuccess;
-      if (!idle) cudaGetLastError();  // cudaErrorNotReady is not an error
-      if (idle) {
-        next = (next + t + 1) % count;
+      if (!idle) {
+        cudaGetLastError();  // cudaErrorNotReady is not an error
+        continue;
+      }
+      if (c.cap[0] >= op_bytes && c.cap[1] >= op_bytes) {
+        next = (unsigned)((i + 1) % count);
         return c;
       }
+      if (idle_any < 0) idle_any = i;
+    }
+    if (idle_any >= 0) {
+      next = (unsigned)((idle_any + 1) % count);
+      return ws[idle_any];
     }
     return ws[next++ % count];
   };
@@ -827,6 +843,12 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   }
   // serialise against the previous Ozaki GEMM (possibly on another stream): the slice buffers are shared
   if (w.used) GPC_CUDA_CHECK(cudaStreamWaitEvent(s, w.done, 0));
+  if (shared_ws && rotate_big) {
+    const size_t rows = (size_t)(c.m > c.n ? c.m : c.n);
+    if (op_bytes > g_oz_big_hw_bytes[dev]) g_oz_big_hw_bytes[dev] = op_bytes;
+    if (rows > g_oz_big_hw_rows[dev]) g_oz_big_hw_rows[dev] = rows;
+    for (int i = 0; i < 2; i++) GPC_CHECK(ensure_ws(w, i, g_oz_big_hw_bytes[dev], g_oz_big_hw_rows[dev]));
+  }
   const bool same = (c.A == c.B && c.lda == c.ldb && c.a_kc == c.b_kc && c.m == c.n);
   GPC_CHECK(slice_operand(w, 0, c.A, c.lda, c.a_kc, c.m, c.k, S, s, launches, c.ktri ? 1 : c.a_tri));
   if (!same) GPC_CHECK(slice_operand(w, 1, c.B, c.ldb, c.b_kc, c.n, c.k, S, s, launches, c.b_tri));
@@ -1200,6 +1222,7 @@ int oz_bench_imma_peak_sustained(int device, int nwide, double seconds, double* 
 void oz_release_device(int dev) {
   if (dev < 0 || dev >= 64) return;
   std::lock_guard<std::mutex> lk(g_oz_mu);
+  g_oz_big_hw_bytes[dev] = g_oz_big_hw_rows[dev] = 0;
   for (int b = 0; b < OZ_BIG; b++) {
     OzWorkspace& w = g_oz_ws[dev][b];
     for (int i = 0; i < 2; i++) {
