@@ -138,7 +138,10 @@ int gpc_posterior(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, const double*
 
 /* One full evaluation = what one SCG step asks of CGp (COptimisable.cpp:309-349):
  * K build -> jitChol -> K^-1 -> alpha -> ll terms -> gradient.  out[0]=logdet, out[1]=quad, out[2]=jitter used.
- * flags: bit0 = also compute gX (needs gX != NULL). Single host sync at the end. */
+ * flags: bit0 = also compute gX (needs gX != NULL). Single host sync at the end.
+ * Afterwards the context holds L, W = L^-1, alpha and the LOWER triangle of K^-1 (gpc_download(GPC_MAT_KINV) returns the
+ * full symmetric matrix); K was factored in the buffer it was built in and is rebuilt from this evaluation's kernel by
+ * whoever needs it next (gpc_download(GPC_MAT_K), gpc_potrf, gpc_jitchol, gpc_add_diag).  alpha = W'(W m). */
 int gpc_eval(gpc_ctx* ctx, const gpc_kcomp* comps, int ncomp, int flags, double* out, double* gparams, double* gX);
 
 enum gpc_which { GPC_MAT_K = 0, GPC_MAT_L = 1, GPC_MAT_KINV = 2, GPC_MAT_ALPHA = 3, GPC_MAT_M = 4 };
