@@ -72,7 +72,7 @@ SYMBOLS = [
     "gpc_solve_alpha", "gpc_inverse", "gpc_alpha_from_inverse", "gpc_grad", "gpc_kern_grad", "gpc_kern_grad_cross", "gpc_posterior",
     "gpc_eval", "gpc_download", "gpc_last_timings", "gpc_last_enqueue_ms", "gpc_dpotrf", "gpc_dpotri", "gpc_dtrsm", "gpc_dsyrk",
     "gpc_dgemm", "gpc_dsymv", "gpc_dsyr", "gpc_bench_dmma_peak", "gpc_bench_imma_peak", "gpc_bench_imma_peak_sustained", "gpc_bench_syrk", "gpc_ctx_set_profile", "gpc_last_gemm_profile", "gpc_last_gemm_profile_split", "gpc_bench_gemm",
-    "gpc_bench_leaf", "gpc_bench_oz_stamps", "gpc_ctx_dims", "gpc_gp_optimise_scg", "gpc_scg_minimise", "gpc_svml_dims", "gpc_svml_read", "gpc_set_gemm_engine", "gpc_gemm_engine_slices", "gpc_gemm_check", "gpc_oz_slice_check",
+    "gpc_bench_leaf", "gpc_bench_oz_stamps", "gpc_ctx_dims", "gpc_gp_optimise_scg", "gpc_scg_minimise", "gpc_svml_dims", "gpc_svml_read", "gpc_set_gemm_engine", "gpc_gemm_engine_slices", "gpc_gemm_check", "gpc_oz_slice_check", "gpc_oz_wave_cuts",
     "gpc_gp_model_read", "gpc_gp_model_write", "gpc_gp_model_check_roundtrip", "gpc_gplvm_model_read",
     "gpc_gplvm_model_write",
     "gpc_sparse_create", "gpc_sparse_destroy", "gpc_sparse_set_data", "gpc_sparse_eval", "gpc_sparse_posterior",

@@ -30,6 +30,7 @@
 #include <string.h>
 #include <map>
 #include <mutex>
+#include <vector>
 #include "common.cuh"
 
 #define GPC_CHECK(expr)            \
@@ -795,6 +796,38 @@ static int slice_operand(OzWorkspace& w, int which, const double* g, int64_t ld,
   return GPC_OK;
 }
 
+// Wave-by-wave launches (GemmCall::sm_limit): cut the linear tile range of oz_gemm_kernel (grouped raster: groups of 8
+// row tiles, column by column; tile t -> group t / (8 tiles_n), column (t % (8 tiles_n)) / gsz, row first + rem % gsz) at
+// column boundaries so that no launch holds more than `limit` NON-EMPTY tiles (lower mode: a tile (bm, bn) exists iff
+// bn <= 2 bm + 1; the others exit at once).  Returns the launch boundaries, first 0, last tiles_m * tiles_n.
+std::vector<int64_t> oz_wave_cuts(int tiles_m, int tiles_n, bool lower, int limit) {
+  std::vector<int64_t> cuts;
+  cuts.push_back(0);
+  const int64_t ntiles = (int64_t)tiles_m * tiles_n;
+  if (limit > 0 && ntiles > limit) {
+    const int GM = 8;
+    int64_t live = 0;
+    for (int first = 0; first < tiles_m; first += GM) {
+      const int gsz = (tiles_m - first) < GM ? (tiles_m - first) : GM;
+      const int64_t gbase = (int64_t)(first / GM) * GM * tiles_n;
+      for (int bn = 0; bn < tiles_n; bn++) {
+        int cnt = gsz;
+        if (lower) {
+          cnt = 0;
+          for (int r = 0; r < gsz; r++) cnt += (bn <= 2 * (first + r) + 1) ? 1 : 0;
+        }
+        if (live + cnt > limit && live > 0) {
+          cuts.push_back(gbase + (int64_t)bn * gsz);
+          live = 0;
+        }
+        live += cnt;
+      }
+    }
+  }
+  cuts.push_back(ntiles);
+  return cuts;
+}
+
 int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int slices) {
   oz_init_settings();
   int dev = 0;
@@ -887,32 +920,7 @@ int launch_gemm_ozaki(const GemmCall& c, cudaStream_t s, int64_t* launches, int 
   // |d| <= 128: (6 * 2^14 + 2 * 65 * 128) * k < 2^31  ->  k <= 18683: chunks of 128 k-blocks (16384)
   const int kchunk = 128;
   const double beta0 = c.beta;
-  // wave-by-wave launches (GemmCall::sm_limit): cut the linear tile range (grouped raster: groups of 8 row tiles, column
-  // by column) at column boundaries so that no launch holds more than sm_limit NON-EMPTY tiles (lower mode: a tile
-  // (bm, bn) exists iff bn <= 2 bm + 1; the others exit at once)
-  std::vector<int64_t> cuts;
-  cuts.push_back(0);
-  if (c.sm_limit > 0 && ntiles > c.sm_limit) {
-    const int GM = 8;
-    int64_t live = 0;
-    for (int first = 0; first < a.tiles_m; first += GM) {
-      const int gsz = (a.tiles_m - first) < GM ? (a.tiles_m - first) : GM;
-      const int64_t gbase = (int64_t)(first / GM) * GM * a.tiles_n;
-      for (int bn = 0; bn < a.tiles_n; bn++) {
-        int cnt = gsz;
-        if (a.lower) {
-          cnt = 0;
-          for (int r = 0; r < gsz; r++) cnt += (bn <= 2 * (first + r) + 1) ? 1 : 0;
-        }
-        if (live + cnt > c.sm_limit && live > 0) {
-          cuts.push_back(gbase + (int64_t)bn * gsz);
-          live = 0;
-        }
-        live += cnt;
-      }
-    }
-  }
-  cuts.push_back(ntiles);
+  const std::vector<int64_t> cuts = oz_wave_cuts(a.tiles_m, a.tiles_n, a.lower != 0, c.sm_limit);
   for (int kb = 0; kb < a.kblocks; kb += kchunk) {
     a.kb_lo = kb;
     a.kb_hi = (kb + kchunk < a.kblocks) ? kb + kchunk : a.kblocks;
@@ -1260,6 +1268,17 @@ extern "C" int gpc_bench_imma_peak(int device, int nwide, double* tops) { return
 // whatever clock the power cap leaves (the roofline of a kernel timed inside a long step); *mhz_hint is not measured here
 extern "C" int gpc_bench_imma_peak_sustained(int device, int nwide, double seconds, double* tops) {
   return gpc::oz_bench_imma_peak_sustained(device, nwide, seconds, tops);
+}
+
+/* host-only: the launch boundaries of a wave-limited product (CPU test of the schedule); returns the number of
+ * boundaries written (<= cap), or the number needed when cuts == NULL */
+extern "C" int gpc_oz_wave_cuts(int tiles_m, int tiles_n, int lower, int limit, long long* cuts, int cap) {
+  if (tiles_m < 1 || tiles_n < 1) return GPC_ERR_ARG;
+  const std::vector<int64_t> v = gpc::oz_wave_cuts(tiles_m, tiles_n, lower != 0, limit);
+  if (!cuts) return (int)v.size();
+  int n = 0;
+  for (; n < (int)v.size() && n < cap; n++) cuts[n] = (long long)v[(size_t)n];
+  return n;
 }
 
 extern "C" int gpc_oz_slice_check(int device, int64_t R, int64_t K, int kc, int S, const double* X, signed char* slices_out,

@@ -372,6 +372,10 @@ int gpc_gemm_engine_slices(void);
 int gpc_gemm_check(int device, int64_t m, int64_t n, int64_t k, int a_kc, int b_kc, int lower, int cfg, double alpha,
                    double beta, const double* A, const double* B, double* C);
 
+/* host-only test hook: launch boundaries of a product on the tensor-core engine that may hold at most `limit` SMs at a
+ * time (tiles_m x tiles_n tiles of 128 x 64, lower: only tiles that intersect the lower triangle are live).  cuts == NULL:
+ * returns the number of boundaries; else writes up to cap of them (first 0, last tiles_m * tiles_n). */
+int gpc_oz_wave_cuts(int tiles_m, int tiles_n, int lower, int limit, long long* cuts, int cap);
 /* The Ozaki splitting of one HOST operand (R rows = the m or n index, K deep; kc: k contiguous, ld K, else ld R):
  * slices_out receives S planes of R x K int8 (k contiguous), scale_out the R row scales 2^e_r, such that
  * x[r,k] = scale[r] * sum_p slices[p][r][k] * 2^-(8p+6) (p = 0..S-1) to 6+8(S-1) bits.  Test hook of the slicing kernel. */
