@@ -218,10 +218,14 @@ int potri_rec(const Dense& d, const double* L, int64_t ldl, int64_t n, double* O
 // reference lapack.h:59-73), but all of it in calls large enough for the tensor-core engine.
 //   node(A, n):  node(A11) -> L11, W11
 //                L21 = A21 W11'                 (main stream, via tmpL: the product cannot be formed in place)
-//                T   = L21 W11                  (side stream, needed only for W21)
+//                T   = L21 W11                  (side stream, needed only for W21; a large one on the bulk stream)
 //                A22 -= L21 L21'                (SYRK)
 //                node(A22) -> L22, W22
 //                W21 = -W22 T
+// Inside gpc_eval (N <= 16384) the stream this runs on is the context's high-priority chain stream and d.bulk its
+// low-priority bulk stream (wave-limited products, GemmCall::sm_limit); two optional restructurings of the TOP level hang
+// off hooks in the recursion: TopFront (look-ahead of the a-columns of L21, on by default) and TopPipe (row-block
+// pipeline of W21 / K^-1, off by default) -- DESIGN.md 4.3 "How one evaluation is scheduled".
 // ------------------------------------------------------------------------------------------------------
 size_t potrf_inv_tspace(int64_t n) {
   if (n <= TILE) return 0;
