@@ -615,6 +615,9 @@ def main():
             "int8_mmas_per_fp64_mma": S * (S + 1) // 2,
             "launches_per_eval": oz_n, "kernel_ms_per_eval": oz_ms, "algorithmic_flops": oz_fl,
             "share_of_step": oz_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
+            "kernel_only_note": "achieved / kernel_ms_per_eval bracket each engine call INCLUDING its slicing kernels (measured "
+                                "live, above); oz_gemm_kernel alone is 6.18 ms of a C2 evaluation in the CUPTI timeline "
+                                "(profiles/timeline_c2_r02.txt) = 86 TFLOP/s-equivalent",
         }
     else:
         ach = dm_fl / (dm_ms * 1e-3) / 1e12 if dm_ms else 0.0
